@@ -1,0 +1,233 @@
+"""Host-side mirror of the hot path's operator surface, over the C ABI only.
+
+Names follow the reference's domain (north_star: src/kmer.rs, src/counter.rs — not in
+the mount, DESIGN.md §2 is the spec): k-mers, spanning k-mer entries, read streams,
+per-sample counts, de novo calls.  Everything that computes goes through libdkb.so;
+there is no NumPy/PyTorch compute path here.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import Stats, Thresholds, Tuning, check, u8p, u16p, u32p, u64p
+
+CHILD, MOTHER, FATHER = 0, 1, 2
+REF, ALT = 0, 1
+CALL_DENOVO, CALL_CHILD_LOW, CALL_MOTHER_ALT, CALL_FATHER_ALT, CALL_PARENT_UNCOVERED = (
+    0x01, 0x02, 0x04, 0x08, 0x10)
+DEFAULT_THRESHOLDS = (3, 2, 0, 1)
+DEFAULT_MIN_BASEQ = 20
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+# ---- kmer.rs primitives -----------------------------------------------------------
+def kmer_encode(seq: str, k: int = None) -> int:
+    k = len(seq) if k is None else k
+    out = C.c_uint64(0)
+    check(_lib.lib().dkb_kmer_encode(seq.encode(), k, C.byref(out)))
+    return int(out.value)
+
+
+def kmer_revcomp(fwd: int, k: int) -> int:
+    return int(_lib.lib().dkb_kmer_revcomp(int(fwd), k))
+
+
+def kmer_canonical(fwd: int, k: int) -> int:
+    return int(_lib.lib().dkb_kmer_canonical(int(fwd), k))
+
+
+# ---- packed read stream -------------------------------------------------------------
+@dataclass
+class ReadStream:
+    """2-bit bases + 1-bit validity flags with one flag-0 separator after every read."""
+    bases2: np.ndarray  # uint32
+    mask1: np.ndarray   # uint32
+    n_positions: int
+    n_bases: int        # read bases only (the throughput unit), separators excluded
+
+
+def stream_words(n_positions: int):
+    L = _lib.lib()
+    return int(L.dkb_stream_bases_words(n_positions)), int(L.dkb_stream_mask_words(n_positions))
+
+
+def pack_reads(seq, qual, offsets, min_baseq: int = DEFAULT_MIN_BASEQ, pinned: bool = False):
+    """seq/qual: uint8 arrays of concatenated reads (qual may be None);
+    offsets: uint64[n_reads + 1].  Returns a ReadStream in host memory."""
+    L = _lib.lib()
+    seq = np.ascontiguousarray(seq, dtype=np.uint8)
+    qual = None if qual is None else np.ascontiguousarray(qual, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n_reads = len(offsets) - 1
+    n_pos = int(L.dkb_stream_positions(_p(offsets, u64p), n_reads))
+    bw, mw = stream_words(n_pos)
+    if pinned:
+        import torch
+        tb = torch.empty(max(bw, 1), dtype=torch.int32).pin_memory()
+        tm = torch.empty(max(mw, 1), dtype=torch.int32).pin_memory()
+        bases2 = tb.numpy().view(np.uint32)
+        mask1 = tm.numpy().view(np.uint32)
+    else:
+        bases2 = np.empty(max(bw, 1), dtype=np.uint32)
+        mask1 = np.empty(max(mw, 1), dtype=np.uint32)
+    out = C.c_uint64(0)
+    check(L.dkb_pack_reads(_p(seq, u8p), _p(qual, u8p), _p(offsets, u64p), n_reads, min_baseq,
+                           _p(bases2, u32p), _p(mask1, u32p), C.byref(out)))
+    n_bases = int(offsets[-1] - offsets[0]) if n_reads else 0
+    return ReadStream(bases2, mask1, int(out.value), n_bases)
+
+
+# ---- spanning k-mer entries -----------------------------------------------------------
+@dataclass
+class KmerEntries:
+    keys: np.ndarray       # uint64 canonical
+    variant: np.ndarray    # uint32
+    allele: np.ndarray     # uint8
+    win_index: np.ndarray = None  # uint16 (bit 15: haplotype window is the key's rc)
+    win_count: np.ndarray = None  # uint16
+    n_variants: int = 0
+
+    def __len__(self):
+        return len(self.keys)
+
+
+def variant_kmers(variants, k: int, drop_shared: bool = True) -> KmerEntries:
+    """variants: sequence of (left_flank, ref, alt, right_flank) strings."""
+    L = _lib.lib()
+    n = len(variants)
+    arrs = []
+    for col in range(4):
+        a = (C.c_char_p * max(n, 1))()
+        for i, v in enumerate(variants):
+            a[i] = v[col].encode()
+        arrs.append(a)
+    n_out = C.c_size_t(0)
+    check(L.dkb_variant_kmers(*arrs, n, k, int(drop_shared), None, None, None, None, None,
+                              C.byref(n_out)))
+    m = int(n_out.value)
+    keys = np.zeros(max(m, 1), dtype=np.uint64)
+    var = np.zeros(max(m, 1), dtype=np.uint32)
+    al = np.zeros(max(m, 1), dtype=np.uint8)
+    wi = np.zeros(max(m, 1), dtype=np.uint16)
+    wc = np.zeros(max(m, 1), dtype=np.uint16)
+    check(L.dkb_variant_kmers(*arrs, n, k, int(drop_shared), _p(keys, u64p), _p(var, u32p),
+                              _p(al, u8p), _p(wi, u16p), _p(wc, u16p), C.byref(n_out)))
+    return KmerEntries(keys[:m], var[:m], al[:m], wi[:m], wc[:m], n)
+
+
+# ---- the counter -----------------------------------------------------------------------
+class KmerCounter:
+    """One GPU context: build the spanning-k-mer table, stream read batches per
+    sample, fetch per-entry / per-variant counts and de novo calls."""
+
+    def __init__(self, k: int, device: int = 0, tuning=None):
+        self._L = _lib.lib()
+        self._h = C.c_void_p()
+        self.k = k
+        self.device = device
+        check(self._L.dkb_ctx_create(device, k, C.byref(self._h)))
+        if tuning is not None:
+            self.set_tuning(*tuning)
+        self.n_entries = 0
+        self.n_variants = 0
+        self._keep = []  # host buffers of in-flight submits
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.dkb_ctx_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _ck(self, code):
+        check(code, self._h)
+
+    def set_tuning(self, seed_len=0, stride=0, bloom_hashes=0):
+        t = Tuning(seed_len, stride, bloom_hashes)
+        self._ck(self._L.dkb_ctx_set_tuning(self._h, C.byref(t)))
+
+    def tuning(self):
+        t = Tuning()
+        self._ck(self._L.dkb_ctx_get_tuning(self._h, C.byref(t)))
+        return t.seed_len, t.stride, t.bloom_hashes
+
+    def build_table(self, entries: KmerEntries, use_window_hints: bool = True):
+        keys = np.ascontiguousarray(entries.keys, dtype=np.uint64)
+        var = np.ascontiguousarray(entries.variant, dtype=np.uint32)
+        al = np.ascontiguousarray(entries.allele, dtype=np.uint8)
+        wi = wc = None
+        if use_window_hints and entries.win_index is not None and entries.win_count is not None:
+            wi = np.ascontiguousarray(entries.win_index, dtype=np.uint16)
+            wc = np.ascontiguousarray(entries.win_count, dtype=np.uint16)
+        self._ck(self._L.dkb_table_build(self._h, _p(keys, u64p), _p(var, u32p), _p(al, u8p),
+                                         _p(wi, u16p), _p(wc, u16p), len(keys),
+                                         int(entries.n_variants)))
+        self.n_entries = len(keys)
+        self.n_variants = int(entries.n_variants)
+
+    def submit(self, stream: ReadStream, sample: int):
+        """Host buffers: async H2D copy + scan; buffers are kept alive until sync()."""
+        self._keep.append(stream)
+        self._ck(self._L.dkb_batch_submit(self._h, stream.bases2.ctypes.data,
+                                          stream.mask1.ctypes.data, stream.n_positions, sample))
+
+    def submit_device(self, d_bases2: int, d_mask1: int, n_positions: int, sample: int):
+        """Device pointers (ints) of a resident stream."""
+        self._ck(self._L.dkb_batch_submit_device(self._h, d_bases2, d_mask1, n_positions, sample))
+
+    def sync(self):
+        self._ck(self._L.dkb_sync(self._h))
+        self._keep.clear()
+
+    def reset_counts(self):
+        self._ck(self._L.dkb_counts_reset(self._h))
+
+    def entry_counts(self) -> np.ndarray:
+        out = np.zeros((3, max(self.n_entries, 1)), dtype=np.uint32)
+        self._ck(self._L.dkb_entry_counts_fetch(self._h, _p(out, u32p)))
+        self._keep.clear()
+        return out[:, : self.n_entries]
+
+    def entry_counts_device(self):
+        """(device pointer, number of uint32) of the [3][n_entries] counters."""
+        p = C.c_void_p()
+        n = C.c_size_t(0)
+        self._ck(self._L.dkb_entry_counts_device(self._h, C.byref(p), C.byref(n)))
+        return int(p.value or 0), int(n.value)
+
+    def finalise(self, thresholds=DEFAULT_THRESHOLDS):
+        t = Thresholds(*[int(x) for x in thresholds])
+        self._ck(self._L.dkb_finalise(self._h, C.byref(t)))
+        nv = max(self.n_variants, 1)
+        hits = np.zeros((nv, 2, 3), dtype=np.uint32)
+        dist = np.zeros((nv, 2, 3), dtype=np.uint32)
+        nk = np.zeros((nv, 2), dtype=np.uint32)
+        calls = np.zeros(nv, dtype=np.uint8)
+        self._ck(self._L.dkb_results_fetch(self._h, _p(hits, u32p), _p(dist, u32p), _p(nk, u32p),
+                                           _p(calls, u8p)))
+        n = self.n_variants
+        return hits[:n], dist[:n], nk[:n], calls[:n]
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._ck(self._L.dkb_stats_get(self._h, C.byref(s)))
+        return {f: getattr(s, f) for f, _ in Stats._fields_}
+
+    def profile_counters(self, enable: bool):
+        self._ck(self._L.dkb_profile_counters(self._h, int(enable)))
+
+    def scan_stream(self) -> int:
+        p = C.c_void_p()
+        self._ck(self._L.dkb_scan_stream(self._h, C.byref(p)))
+        return int(p.value or 0)

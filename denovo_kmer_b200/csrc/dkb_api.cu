@@ -1,0 +1,571 @@
+// dkb_api.cu — the C ABI of include/dkb.h over the sm_100a kernels.
+// No CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/dkb.h"
+#include "dkb_build.cuh"
+#include "dkb_scan.cuh"
+
+using namespace dkb;
+
+struct dkb_ctx {
+  int device = 0;
+  int k = 0;
+  int n_sms = 0;
+  std::string err;
+
+  dkb_tuning user_tuning{0, 0, 0};
+  int s = 0, D = 0, NH = 0;  // resolved at table build
+
+  // entries
+  size_t n_entries = 0, n_live = 0;
+  uint32_t n_variants = 0;
+  uint64_t *d_keys = nullptr;
+  uint32_t *d_variant = nullptr;
+  uint8_t *d_allele = nullptr;
+  uint8_t *d_dead = nullptr;
+  // key table
+  uint64_t *d_tkeys = nullptr;
+  uint32_t *d_tentry = nullptr;
+  uint64_t *d_toffs = nullptr;
+  uint32_t table_slots = 0;
+  // seeds
+  uint64_t *d_seedtab = nullptr;
+  uint32_t seed_slots = 0;
+  uint32_t n_seeds = 0;
+  uint32_t *d_bloom = nullptr;
+  uint64_t bloom_bits_set = 0;
+  // counters and results
+  uint32_t *d_counts = nullptr;  // [3][n_entries]
+  uint32_t *d_hits = nullptr, *d_distinct = nullptr, *d_nkmers = nullptr;
+  uint8_t *d_calls = nullptr;
+  bool finalised = false;
+  // profiling counters
+  bool prof = false;
+  unsigned long long *d_prof = nullptr;
+  // streams / staging for host batches
+  cudaStream_t s_scan = nullptr, s_copy = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  bool have_timing = false;
+  struct Stage {
+    uint32_t *bases = nullptr, *mask = nullptr;
+    size_t bases_cap = 0, mask_cap = 0;  // in words
+    cudaEvent_t copied = nullptr, freed = nullptr;
+    bool in_use = false;
+  } stage[2];
+  int next_stage = 0;
+  uint64_t scan_launches = 0, positions_scanned = 0;
+  bool smem_attr_set = false;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(dkb_ctx *ctx, int code, const std::string &msg) {
+  if (ctx) ctx->err = msg;
+  g_err = msg;
+  return code;
+}
+
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? DKB_ENOMEM : DKB_ECUDA,          \
+                  std::string(#call) + ": " + cudaGetErrorString(e_));                    \
+  } while (0)
+
+uint32_t pow2_at_least(uint64_t x) {
+  uint32_t p = 1024;
+  while (p < x && p < 0x80000000u) p <<= 1;
+  return p;
+}
+
+template <typename T>
+void dfree(T *&p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+void free_table(dkb_ctx *c) {
+  dfree(c->d_keys); dfree(c->d_variant); dfree(c->d_allele); dfree(c->d_dead);
+  dfree(c->d_tkeys); dfree(c->d_tentry); dfree(c->d_toffs);
+  dfree(c->d_seedtab); dfree(c->d_bloom);
+  dfree(c->d_counts); dfree(c->d_hits); dfree(c->d_distinct); dfree(c->d_nkmers);
+  dfree(c->d_calls);
+  c->n_entries = c->n_live = 0;
+  c->n_variants = 0;
+  c->finalised = false;
+}
+
+// Resolve (s, D, NH): the caller's choice, else DKB_TUNING="s,D,NH", else auto.
+int resolve_tuning(dkb_ctx *ctx, size_t n_entries) {
+  dkb_tuning t = ctx->user_tuning;
+  if (const char *e = getenv("DKB_TUNING")) {
+    int a = 0, b = 0, c = 0;
+    if (sscanf(e, "%d,%d,%d", &a, &b, &c) >= 1) {
+      if (!t.seed_len) t.seed_len = a;
+      if (!t.stride) t.stride = b;
+      if (!t.bloom_hashes) t.bloom_hashes = c;
+    }
+  }
+  const int k = ctx->k;
+  int D = t.stride;
+  if (D == 0) D = 1;
+  if (D != 1 && D != 2 && D != 4) return fail(ctx, DKB_EINVAL, "stride must be 1, 2 or 4");
+  int s = t.seed_len;
+  if (s == 0) {
+    s = k - D + 1 < 16 ? k - D + 1 : 16;
+    // keep a ladder of exactly two seeds per strand possible: spacing floor((k-s+1)/D)*D
+    if (D == 4 && s > 14 && k - 14 + 1 >= 16) s = 14;
+    if (D == 2 && s > 15 && k - 15 + 1 >= 16) s = 15;
+  }
+  if (s < 8 || s > 16 || s > k - D + 1) return fail(ctx, DKB_EINVAL, "seed_len out of range");
+  int NH = t.bloom_hashes;
+  if (NH == 0) {
+    // two bits per seed pay once the filter holds more than ~1 seed per 50 bits
+    const double est_seeds = (double)n_entries * 0.25 * D;
+    NH = (s >= 11 && est_seeds > BLOOM_WORDS * 32 / 50.0) ? 2 : 1;
+  }
+  if (NH != 1 && NH != 2) return fail(ctx, DKB_EINVAL, "bloom_hashes must be 1 or 2");
+  if (NH == 2 && s < 11) return fail(ctx, DKB_EINVAL, "bloom_hashes=2 needs seed_len >= 11");
+  ctx->s = s;
+  ctx->D = D;
+  ctx->NH = NH;
+  return DKB_OK;
+}
+
+typedef void (*scan_fn)(const ScanParams);
+
+scan_fn pick_scan(int D, int NH, bool prof) {
+#define PICK(d, h)                                                         \
+  if (D == d && NH == h) return prof ? (scan_fn)k_scan<d, h, true> : (scan_fn)k_scan<d, h, false>;
+  PICK(1, 1) PICK(1, 2) PICK(2, 1) PICK(2, 2) PICK(4, 1) PICK(4, 2)
+#undef PICK
+  return nullptr;
+}
+
+int launch_scan(dkb_ctx *ctx, const uint32_t *d_bases, const uint32_t *d_mask,
+                uint64_t n_positions, int sample) {
+  ScanParams P;
+  P.bases = d_bases;
+  P.mask = d_mask;
+  P.n_pos = (uint32_t)n_positions;
+  P.n_bwords = (uint32_t)dkb_stream_bases_words(n_positions);
+  P.n_mwords = (uint32_t)dkb_stream_mask_words(n_positions);
+  P.n_tiles = (uint32_t)((n_positions + WTILE - 1) / WTILE);
+  P.bloom = ctx->d_bloom;
+  P.seedtab = ctx->d_seedtab;
+  P.seedtab_mask = ctx->seed_slots - 1;
+  P.seed_mult = ctx->s == 16 ? SEED_MULT : SEED_MULT << (32 - 2 * ctx->s);
+  P.seed_mask = ctx->s == 16 ? 0xFFFFFFFFu : ((1u << (2 * ctx->s)) - 1);
+  P.tkeys = ctx->d_tkeys;
+  P.tentry = ctx->d_tentry;
+  P.toffs = ctx->d_toffs;
+  P.table_mask = ctx->table_slots - 1;
+  P.counts = ctx->d_counts + (size_t)sample * ctx->n_entries;
+  P.k = ctx->k;
+  P.prof = ctx->d_prof;
+  scan_fn fn = pick_scan(ctx->D, ctx->NH, ctx->prof);
+  if (!fn) return fail(ctx, DKB_EINVAL, "no scan kernel for this tuning");
+  CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)SCAN_SMEM_BYTES));
+  uint32_t grid = (P.n_tiles + SCAN_WARPS - 1) / SCAN_WARPS;
+  if (grid > (uint32_t)ctx->n_sms) grid = ctx->n_sms;
+  if (grid == 0) return DKB_OK;
+  CU(cudaEventRecord(ctx->ev_start, ctx->s_scan));
+  fn<<<grid, SCAN_THREADS, SCAN_SMEM_BYTES, ctx->s_scan>>>(P);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(ctx->ev_stop, ctx->s_scan));
+  ctx->have_timing = true;
+  ctx->scan_launches++;
+  ctx->positions_scanned += n_positions;
+  ctx->finalised = false;
+  return DKB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dkb_abi_version(void) { return DKB_ABI_VERSION; }
+
+const char *dkb_strerror(int code) {
+  switch (code) {
+    case DKB_OK: return "ok";
+    case DKB_EINVAL: return "invalid argument";
+    case DKB_ECUDA: return "CUDA error";
+    case DKB_ENOMEM: return "out of memory";
+    case DKB_ESTATE: return "call out of order";
+    case DKB_ENODEV: return "no usable CUDA device (no CPU fallback exists)";
+    default: return "unknown error";
+  }
+}
+
+const char *dkb_last_error(const dkb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+int dkb_ctx_create(int device, int k, dkb_ctx **out) {
+  dkb_ctx *ctx = nullptr;
+  if (!out) return fail(nullptr, DKB_EINVAL, "out is null");
+  *out = nullptr;
+  if (k < DKB_MIN_K || k > DKB_MAX_K) return fail(nullptr, DKB_EINVAL, "k out of range [8, 31]");
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, DKB_ENODEV, "no CUDA device; this library has no CPU fallback");
+  }
+  if (device < 0 || device >= n_dev) return fail(nullptr, DKB_EINVAL, "device index out of range");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+    return fail(nullptr, DKB_ECUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10)
+    return fail(nullptr, DKB_ENODEV,
+                std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                    "; kernels are built for sm_100a only");
+  ctx = new (std::nothrow) dkb_ctx();
+  if (!ctx) return fail(nullptr, DKB_ENOMEM, "host allocation failed");
+  ctx->device = device;
+  ctx->k = k;
+  ctx->n_sms = prop.multiProcessorCount;
+  int rc = [&]() -> int {
+    CU(cudaSetDevice(device));
+    CU(cudaStreamCreateWithFlags(&ctx->s_scan, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&ctx->ev_start));
+    CU(cudaEventCreate(&ctx->ev_stop));
+    for (auto &st : ctx->stage) {
+      CU(cudaEventCreateWithFlags(&st.copied, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&st.freed, cudaEventDisableTiming));
+    }
+    CU(cudaMalloc(&ctx->d_prof, 4 * sizeof(unsigned long long)));
+    CU(cudaMemset(ctx->d_prof, 0, 4 * sizeof(unsigned long long)));
+    return DKB_OK;
+  }();
+  if (rc != DKB_OK) {
+    g_err = ctx->err;
+    dkb_ctx_destroy(ctx);
+    return rc;
+  }
+  *out = ctx;
+  return DKB_OK;
+}
+
+int dkb_ctx_destroy(dkb_ctx *ctx) {
+  if (!ctx) return DKB_OK;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  free_table(ctx);
+  dfree(ctx->d_prof);
+  for (auto &st : ctx->stage) {
+    dfree(st.bases);
+    dfree(st.mask);
+    if (st.copied) cudaEventDestroy(st.copied);
+    if (st.freed) cudaEventDestroy(st.freed);
+  }
+  if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+  if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
+  if (ctx->s_scan) cudaStreamDestroy(ctx->s_scan);
+  if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
+  delete ctx;
+  return DKB_OK;
+}
+
+int dkb_ctx_set_tuning(dkb_ctx *ctx, const dkb_tuning *tuning) {
+  if (!ctx) return fail(nullptr, DKB_EINVAL, "ctx is null");
+  ctx->user_tuning = tuning ? *tuning : dkb_tuning{0, 0, 0};
+  return DKB_OK;
+}
+
+int dkb_ctx_get_tuning(const dkb_ctx *ctx, dkb_tuning *out) {
+  if (!ctx || !out) return fail(nullptr, DKB_EINVAL, "null argument");
+  out->seed_len = ctx->s;
+  out->stride = ctx->D;
+  out->bloom_hashes = ctx->NH;
+  return DKB_OK;
+}
+
+int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_ids,
+                    const uint8_t *allele_ids, const uint16_t *win_index,
+                    const uint16_t *win_count, size_t n, uint32_t n_variants) {
+  if (!ctx) return fail(nullptr, DKB_EINVAL, "ctx is null");
+  if (n && (!keys || !variant_ids || !allele_ids)) return fail(ctx, DKB_EINVAL, "null entry array");
+  if (n >= 0x40000000ull) return fail(ctx, DKB_EINVAL, "too many entries (max 2^30 - 1)");
+  if ((win_index == nullptr) != (win_count == nullptr))
+    return fail(ctx, DKB_EINVAL, "win_index and win_count must be given together");
+  const uint64_t km = kmer_mask(ctx->k);
+  for (size_t i = 0; i < n; i++) {
+    if (keys[i] > km) return fail(ctx, DKB_EINVAL, "key wider than 2k bits");
+    if (variant_ids[i] >= n_variants) return fail(ctx, DKB_EINVAL, "variant id out of range");
+    if (allele_ids[i] >= DKB_N_ALLELES) return fail(ctx, DKB_EINVAL, "allele id must be 0 or 1");
+    if (win_index && ((win_index[i] & 0x7FFFu) >= win_count[i]))
+      return fail(ctx, DKB_EINVAL, "win_index >= win_count");
+  }
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->s_scan));
+  CU(cudaStreamSynchronize(ctx->s_copy));
+  free_table(ctx);
+  int rc = resolve_tuning(ctx, n);
+  if (rc != DKB_OK) return rc;
+
+  ctx->n_entries = n;
+  ctx->n_variants = n_variants;
+  const size_t n1 = n ? n : 1, nv1 = n_variants ? n_variants : 1;
+  ctx->table_slots = pow2_at_least(2 * (uint64_t)n + 2);
+  uint16_t *d_wi = nullptr, *d_wc = nullptr;
+  uint32_t *d_slot_of = nullptr;
+  uint64_t *d_tmp = nullptr;
+  unsigned int *d_nseeds = nullptr;
+  cudaStream_t st = ctx->s_scan;
+  auto cleanup = [&]() { dfree(d_wi); dfree(d_wc); dfree(d_slot_of); dfree(d_tmp); dfree(d_nseeds); };
+  rc = [&]() -> int {
+    CU(cudaMalloc(&ctx->d_keys, n1 * 8));
+    CU(cudaMalloc(&ctx->d_variant, n1 * 4));
+    CU(cudaMalloc(&ctx->d_allele, n1));
+    CU(cudaMalloc(&ctx->d_dead, n1));
+    CU(cudaMalloc(&d_slot_of, n1 * 4));
+    CU(cudaMalloc(&ctx->d_tkeys, (size_t)ctx->table_slots * 8));
+    CU(cudaMalloc(&ctx->d_tentry, (size_t)ctx->table_slots * 4));
+    CU(cudaMalloc(&ctx->d_toffs, (size_t)ctx->table_slots * 8));
+    CU(cudaMalloc(&ctx->d_bloom, (size_t)BLOOM_WORDS * 4));
+    CU(cudaMalloc(&ctx->d_counts, n1 * 3 * 4));
+    CU(cudaMalloc(&ctx->d_hits, nv1 * 6 * 4));
+    CU(cudaMalloc(&ctx->d_distinct, nv1 * 6 * 4));
+    CU(cudaMalloc(&ctx->d_nkmers, nv1 * 2 * 4));
+    CU(cudaMalloc(&ctx->d_calls, nv1));
+    CU(cudaMalloc(&d_nseeds, 4));
+    CU(cudaMemsetAsync(ctx->d_tkeys, 0xFF, (size_t)ctx->table_slots * 8, st));
+    CU(cudaMemsetAsync(ctx->d_tentry, 0xFF, (size_t)ctx->table_slots * 4, st));
+    CU(cudaMemsetAsync(ctx->d_toffs, 0, (size_t)ctx->table_slots * 8, st));
+    CU(cudaMemsetAsync(ctx->d_bloom, 0, (size_t)BLOOM_WORDS * 4, st));
+    CU(cudaMemsetAsync(ctx->d_counts, 0, n1 * 3 * 4, st));
+    CU(cudaMemsetAsync(ctx->d_dead, 0, n1, st));
+    CU(cudaMemsetAsync(d_nseeds, 0, 4, st));
+    if (n) {
+      CU(cudaMemcpyAsync(ctx->d_keys, keys, n * 8, cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(ctx->d_variant, variant_ids, n * 4, cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(ctx->d_allele, allele_ids, n, cudaMemcpyHostToDevice, st));
+      if (win_index) {
+        CU(cudaMalloc(&d_wi, n * 2));
+        CU(cudaMalloc(&d_wc, n * 2));
+        CU(cudaMemcpyAsync(d_wi, win_index, n * 2, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_wc, win_count, n * 2, cudaMemcpyHostToDevice, st));
+      }
+    }
+    // seeds: first into an over-sized table, then re-hashed into a right-sized one
+    const uint32_t tmp_slots = pow2_at_least(4 * (uint64_t)n * ctx->D + 2);
+    CU(cudaMalloc(&d_tmp, (size_t)tmp_slots * 8));
+    CU(cudaMemsetAsync(d_tmp, 0, (size_t)tmp_slots * 8, st));
+    BuildParams B;
+    B.keys = ctx->d_keys; B.variant = ctx->d_variant; B.allele = ctx->d_allele;
+    B.win_index = d_wi; B.win_count = d_wc; B.n = (uint32_t)n;
+    B.tkeys = ctx->d_tkeys; B.tentry = ctx->d_tentry; B.toffs = ctx->d_toffs;
+    B.table_mask = ctx->table_slots - 1; B.slot_of = d_slot_of; B.dead = ctx->d_dead;
+    B.k = ctx->k; B.s = ctx->s; B.D = ctx->D;
+    const int TB = 256;
+    if (n) {
+      const uint32_t g1 = (uint32_t)((n + TB - 1) / TB), g2 = (uint32_t)((2 * n + TB - 1) / TB);
+      k_insert_entries<<<g1, TB, 0, st>>>(B);
+      k_mark_repeats<<<g1, TB, 0, st>>>(B);
+      k_apply_dead<<<g1, TB, 0, st>>>(B);
+      k_assign_seeds<<<g2, TB, 0, st>>>(B, d_tmp, tmp_slots - 1, d_nseeds);
+      CU(cudaGetLastError());
+    }
+    unsigned int n_seeds = 0;
+    CU(cudaMemcpyAsync(&n_seeds, d_nseeds, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->n_seeds = n_seeds;
+    ctx->seed_slots = pow2_at_least(3 * (uint64_t)n_seeds + 2);
+    CU(cudaMalloc(&ctx->d_seedtab, (size_t)ctx->seed_slots * 8));
+    CU(cudaMemsetAsync(ctx->d_seedtab, 0, (size_t)ctx->seed_slots * 8, st));
+    const uint32_t seed_mult = ctx->s == 16 ? SEED_MULT : SEED_MULT << (32 - 2 * ctx->s);
+    k_rehash_seeds<<<(tmp_slots + TB - 1) / TB, TB, 0, st>>>(
+        d_tmp, tmp_slots, ctx->d_seedtab, ctx->seed_slots - 1, ctx->d_bloom, seed_mult, ctx->NH);
+    CU(cudaGetLastError());
+    std::vector<uint32_t> bloom(BLOOM_WORDS);
+    std::vector<uint8_t> dead(n1);
+    CU(cudaMemcpyAsync(bloom.data(), ctx->d_bloom, (size_t)BLOOM_WORDS * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(dead.data(), ctx->d_dead, n1, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->bloom_bits_set = 0;
+    for (uint32_t w : bloom) ctx->bloom_bits_set += (uint64_t)__builtin_popcount(w);
+    ctx->n_live = 0;
+    for (size_t i = 0; i < n; i++) ctx->n_live += !dead[i];
+    return DKB_OK;
+  }();
+  cleanup();
+  if (rc != DKB_OK) free_table(ctx);
+  return rc;
+}
+
+int dkb_batch_submit_device(dkb_ctx *ctx, const uint32_t *d_bases2, const uint32_t *d_mask1,
+                            uint64_t n_positions, int sample) {
+  if (!ctx) return fail(nullptr, DKB_EINVAL, "ctx is null");
+  if (!ctx->d_tkeys) return fail(ctx, DKB_ESTATE, "dkb_table_build must come first");
+  if (sample < 0 || sample >= DKB_N_SAMPLES) return fail(ctx, DKB_EINVAL, "sample must be 0, 1 or 2");
+  if (n_positions == 0) return DKB_OK;
+  if (n_positions > 0xFFFFF000ull) return fail(ctx, DKB_EINVAL, "batch too long (max 2^32 - 4096 positions)");
+  if (!d_bases2 || !d_mask1) return fail(ctx, DKB_EINVAL, "null stream pointer");
+  if (((uintptr_t)d_bases2 & 15) || ((uintptr_t)d_mask1 & 3))
+    return fail(ctx, DKB_EINVAL, "bases2 must be 16-byte aligned");
+  CU(cudaSetDevice(ctx->device));
+  return launch_scan(ctx, d_bases2, d_mask1, n_positions, sample);
+}
+
+int dkb_batch_submit(dkb_ctx *ctx, const uint32_t *bases2, const uint32_t *mask1,
+                     uint64_t n_positions, int sample) {
+  if (!ctx) return fail(nullptr, DKB_EINVAL, "ctx is null");
+  if (!ctx->d_tkeys) return fail(ctx, DKB_ESTATE, "dkb_table_build must come first");
+  if (sample < 0 || sample >= DKB_N_SAMPLES) return fail(ctx, DKB_EINVAL, "sample must be 0, 1 or 2");
+  if (n_positions == 0) return DKB_OK;
+  if (n_positions > 0xFFFFF000ull) return fail(ctx, DKB_EINVAL, "batch too long (max 2^32 - 4096 positions)");
+  if (!bases2 || !mask1) return fail(ctx, DKB_EINVAL, "null stream pointer");
+  CU(cudaSetDevice(ctx->device));
+  const size_t bw = dkb_stream_bases_words(n_positions), mw = dkb_stream_mask_words(n_positions);
+  dkb_ctx::Stage &st = ctx->stage[ctx->next_stage];
+  ctx->next_stage ^= 1;
+  if (st.in_use) CU(cudaStreamWaitEvent(ctx->s_copy, st.freed, 0));
+  if (st.bases_cap < bw || st.mask_cap < mw) {
+    // the previous scan may still read the old buffers
+    if (st.in_use) CU(cudaEventSynchronize(st.freed));
+    dfree(st.bases);
+    dfree(st.mask);
+    st.bases_cap = bw + bw / 8 + 64;
+    st.mask_cap = mw + mw / 8 + 64;
+    CU(cudaMalloc(&st.bases, st.bases_cap * 4));
+    CU(cudaMalloc(&st.mask, st.mask_cap * 4));
+  }
+  CU(cudaMemcpyAsync(st.bases, bases2, bw * 4, cudaMemcpyHostToDevice, ctx->s_copy));
+  CU(cudaMemcpyAsync(st.mask, mask1, mw * 4, cudaMemcpyHostToDevice, ctx->s_copy));
+  CU(cudaEventRecord(st.copied, ctx->s_copy));
+  CU(cudaStreamWaitEvent(ctx->s_scan, st.copied, 0));
+  int rc = launch_scan(ctx, st.bases, st.mask, n_positions, sample);
+  if (rc != DKB_OK) return rc;
+  CU(cudaEventRecord(st.freed, ctx->s_scan));
+  st.in_use = true;
+  return DKB_OK;
+}
+
+int dkb_sync(dkb_ctx *ctx) {
+  if (!ctx) return fail(nullptr, DKB_EINVAL, "ctx is null");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->s_copy));
+  CU(cudaStreamSynchronize(ctx->s_scan));
+  return DKB_OK;
+}
+
+int dkb_counts_reset(dkb_ctx *ctx) {
+  if (!ctx) return fail(nullptr, DKB_EINVAL, "ctx is null");
+  if (!ctx->d_counts) return fail(ctx, DKB_ESTATE, "dkb_table_build must come first");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemsetAsync(ctx->d_counts, 0, (ctx->n_entries ? ctx->n_entries : 1) * 3 * 4, ctx->s_scan));
+  CU(cudaMemsetAsync(ctx->d_prof, 0, 4 * sizeof(unsigned long long), ctx->s_scan));
+  ctx->finalised = false;
+  return DKB_OK;
+}
+
+int dkb_entry_counts_fetch(dkb_ctx *ctx, uint32_t *out) {
+  if (!ctx || !out) return fail(ctx, DKB_EINVAL, "null argument");
+  if (!ctx->d_counts) return fail(ctx, DKB_ESTATE, "dkb_table_build must come first");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->s_copy));
+  CU(cudaMemcpyAsync(out, ctx->d_counts, ctx->n_entries * 3 * 4, cudaMemcpyDeviceToHost, ctx->s_scan));
+  CU(cudaStreamSynchronize(ctx->s_scan));
+  return DKB_OK;
+}
+
+int dkb_entry_counts_device(dkb_ctx *ctx, void **d_ptr, size_t *n_u32) {
+  if (!ctx || !d_ptr || !n_u32) return fail(ctx, DKB_EINVAL, "null argument");
+  if (!ctx->d_counts) return fail(ctx, DKB_ESTATE, "dkb_table_build must come first");
+  *d_ptr = ctx->d_counts;
+  *n_u32 = ctx->n_entries * 3;
+  return DKB_OK;
+}
+
+int dkb_finalise(dkb_ctx *ctx, const dkb_thresholds *thr) {
+  if (!ctx || !thr) return fail(ctx, DKB_EINVAL, "null argument");
+  if (!ctx->d_counts) return fail(ctx, DKB_ESTATE, "dkb_table_build must come first");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->s_scan;
+  const size_t nv1 = ctx->n_variants ? ctx->n_variants : 1;
+  CU(cudaMemsetAsync(ctx->d_hits, 0, nv1 * 6 * 4, st));
+  CU(cudaMemsetAsync(ctx->d_distinct, 0, nv1 * 6 * 4, st));
+  CU(cudaMemsetAsync(ctx->d_nkmers, 0, nv1 * 2 * 4, st));
+  const int TB = 256;
+  if (ctx->n_entries)
+    k_variant_reduce<<<(uint32_t)((ctx->n_entries + TB - 1) / TB), TB, 0, st>>>(
+        ctx->d_counts, ctx->d_variant, ctx->d_allele, ctx->d_dead, (uint32_t)ctx->n_entries,
+        ctx->d_hits, ctx->d_distinct, ctx->d_nkmers);
+  Thresholds T{thr->min_child_alt_hits, thr->min_child_alt_distinct, thr->max_parent_alt_hits,
+               thr->min_parent_ref_hits};
+  if (ctx->n_variants)
+    k_calls<<<(ctx->n_variants + TB - 1) / TB, TB, 0, st>>>(ctx->d_hits, ctx->d_distinct,
+                                                            ctx->n_variants, T, ctx->d_calls);
+  CU(cudaGetLastError());
+  ctx->finalised = true;
+  return DKB_OK;
+}
+
+int dkb_results_fetch(dkb_ctx *ctx, uint32_t *hits, uint32_t *distinct, uint32_t *n_kmers,
+                      uint8_t *calls) {
+  if (!ctx) return fail(nullptr, DKB_EINVAL, "ctx is null");
+  if (!ctx->finalised) return fail(ctx, DKB_ESTATE, "dkb_finalise must come first");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->s_scan;
+  const size_t nv = ctx->n_variants;
+  if (hits) CU(cudaMemcpyAsync(hits, ctx->d_hits, nv * 6 * 4, cudaMemcpyDeviceToHost, st));
+  if (distinct) CU(cudaMemcpyAsync(distinct, ctx->d_distinct, nv * 6 * 4, cudaMemcpyDeviceToHost, st));
+  if (n_kmers) CU(cudaMemcpyAsync(n_kmers, ctx->d_nkmers, nv * 2 * 4, cudaMemcpyDeviceToHost, st));
+  if (calls) CU(cudaMemcpyAsync(calls, ctx->d_calls, nv, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return DKB_OK;
+}
+
+int dkb_stats_get(dkb_ctx *ctx, dkb_stats *out) {
+  if (!ctx || !out) return fail(ctx, DKB_EINVAL, "null argument");
+  memset(out, 0, sizeof(*out));
+  CU(cudaSetDevice(ctx->device));
+  out->n_entries = ctx->n_entries;
+  out->n_live_entries = ctx->n_live;
+  out->table_slots = ctx->table_slots;
+  out->n_seeds = ctx->n_seeds;
+  out->seed_slots = ctx->seed_slots;
+  out->bloom_words = BLOOM_WORDS;
+  out->bloom_bits_set = ctx->bloom_bits_set;
+  out->scan_launches = ctx->scan_launches;
+  out->positions_scanned = ctx->positions_scanned;
+  CU(cudaStreamSynchronize(ctx->s_scan));
+  unsigned long long prof[4];
+  CU(cudaMemcpy(prof, ctx->d_prof, sizeof(prof), cudaMemcpyDeviceToHost));
+  out->bloom_hits = prof[0];
+  out->seed_hits = prof[1];
+  out->windows_probed = prof[2];
+  out->window_hits = prof[3];
+  if (ctx->have_timing) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop) == cudaSuccess) out->last_scan_ms = ms;
+    else cudaGetLastError();
+  }
+  return DKB_OK;
+}
+
+int dkb_profile_counters(dkb_ctx *ctx, int enable) {
+  if (!ctx) return fail(nullptr, DKB_EINVAL, "ctx is null");
+  ctx->prof = enable != 0;
+  return DKB_OK;
+}
+
+int dkb_scan_stream(dkb_ctx *ctx, void **stream_out) {
+  if (!ctx || !stream_out) return fail(ctx, DKB_EINVAL, "null argument");
+  *stream_out = (void *)ctx->s_scan;
+  return DKB_OK;
+}
+
+}  // extern "C"

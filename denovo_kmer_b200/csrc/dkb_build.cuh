@@ -1,0 +1,206 @@
+// dkb_build.cuh — kernel 1 (table build) and kernel 3 (finalise).
+//
+// Build = the GPU form of src/counter.rs's "set of k-mers that span each
+// candidate allele" (unmounted): every entry (canonical key,
+// variant, allele) gets a slot in an open-addressing multimap; for both
+// orientations of the key and every stride class one s-mer of the k-mer is
+// designated as its seed and put in the exact seed table and the filter.
+#pragma once
+#include "dkb_device.cuh"
+
+namespace dkb {
+
+struct BuildParams {
+  const uint64_t *keys;
+  const uint32_t *variant;
+  const uint8_t *allele;
+  const uint16_t *win_index;  // may be null: bit 15 = haplotype window is the rc of the key
+  const uint16_t *win_count;  // may be null
+  uint32_t n;
+  uint64_t *tkeys;
+  uint32_t *tentry;
+  uint64_t *toffs;
+  uint32_t table_mask;
+  uint32_t *slot_of;  // [n] slot claimed by each entry
+  uint8_t *dead;      // [n]
+  int k, s, D;
+};
+
+__global__ void k_insert_entries(const BuildParams B) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B.n) return;
+  const uint64_t key = B.keys[i];
+  uint32_t slot = (uint32_t)mix64(key) & B.table_mask;
+  while (true) {
+    const unsigned long long old =
+        atomicCAS(reinterpret_cast<unsigned long long *>(B.tkeys + slot), KEY_EMPTY, key);
+    if (old == KEY_EMPTY) break;
+    slot = (slot + 1) & B.table_mask;
+  }
+  B.tentry[slot] = i;
+  B.slot_of[i] = slot;
+}
+
+// An entry is dead when an earlier entry has the same (key, variant, allele).
+__global__ void k_mark_repeats(const BuildParams B) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B.n) return;
+  const uint64_t key = B.keys[i];
+  uint32_t slot = (uint32_t)mix64(key) & B.table_mask;
+  uint8_t dead = 0;
+  while (true) {
+    const uint64_t tk = B.tkeys[slot];
+    if (tk == KEY_EMPTY) break;
+    if (tk == key) {
+      const uint32_t e = B.tentry[slot];
+      if (e < i && B.variant[e] == B.variant[i] && B.allele[e] == B.allele[i]) {
+        dead = 1;
+        break;
+      }
+    }
+    slot = (slot + 1) & B.table_mask;
+  }
+  B.dead[i] = dead;
+}
+
+__global__ void k_apply_dead(const BuildParams B) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B.n) return;
+  if (B.dead[i]) B.tentry[B.slot_of[i]] = ENTRY_DEAD;
+}
+
+// Insert (seed, offset bit) into an exact seed table; *n_new counts distinct seeds.
+__device__ __forceinline__ void seedtab_insert(uint64_t *tab, uint32_t mask, uint32_t seed,
+                                               uint32_t info, unsigned int *n_new) {
+  uint32_t slot = hash32(seed) & mask;
+  const unsigned long long word = (unsigned long long)info << 32 | seed;
+  while (true) {
+    unsigned long long old = tab[slot];
+    if (old == 0) {
+      old = atomicCAS(reinterpret_cast<unsigned long long *>(tab + slot), 0ull, word);
+      if (old == 0) {
+        if (n_new) atomicAdd(n_new, 1u);
+        return;
+      }
+    }
+    if ((uint32_t)old == seed) {
+      atomicOr(reinterpret_cast<unsigned long long *>(tab + slot),
+               (unsigned long long)info << 32);
+      return;
+    }
+    slot = (slot + 1) & mask;
+  }
+}
+
+// One thread per (entry, orientation): choose the designated seed offset of
+// every stride class, record it in the slot and register the seed.
+//   ladder rule (window hints present): seeds sit on a ladder of spacing
+//     G = floor((k-s+1)/D)*D along the haplotype, so neighbouring windows share
+//     them (2 seeds per SNV haplotype strand at k=31, s=16, D=1);
+//   min-hash rule (no hints): the s-mer of the class with the smallest hash.
+__global__ void k_assign_seeds(const BuildParams B, uint64_t *seedtab, uint32_t seedtab_mask,
+                               unsigned int *n_seeds) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = t >> 1;
+  const int ori = t & 1;
+  if (i >= B.n || B.dead[i]) return;
+  const int k = B.k, s = B.s, D = B.D, E = k - s;
+  const uint64_t km = kmer_mask(k);
+  const uint64_t key = B.keys[i];
+  const uint64_t v0 = base_reverse(key, k);  // stream order of the key's own string
+  const uint64_t v1 = ~key & km;             // stream order of its reverse complement
+  if (ori == 1 && v1 == v0) return;          // palindrome: one orientation only
+  const uint64_t v = ori ? v1 : v0;
+  const uint32_t smask = s == 16 ? 0xFFFFFFFFu : ((1u << (2 * s)) - 1);
+  const bool ladder = B.win_index != nullptr && B.win_count != nullptr;
+  uint32_t u = 0;
+  if (ladder) {
+    const uint32_t wi = B.win_index[i];
+    const uint32_t nwin = B.win_count[i];
+    const int hap_ori = (wi >> 15) & 1;  // orientation whose string reads along the haplotype
+    u = wi & 0x7FFFu;
+    if (ori != hap_ori) u = nwin - 1 - u;  // same window seen on the other strand
+  }
+  uint64_t offs = 0;
+  for (int c = 0; c < D; c++) {
+    int j;
+    if (ladder) {
+      const int G = ((E + 1) / D) * D;
+      const int r = (int)((u + c) % D);
+      const int base = E - ((E - r) % D);  // largest ladder origin <= E in residue r
+      int P = base;
+      if ((int)u > base) P = base + (((int)u - base + G - 1) / G) * G;
+      j = P - (int)u;
+    } else {
+      uint32_t best = 0xFFFFFFFFu;
+      j = c;
+      for (int o = c; o <= E; o += D) {
+        const uint32_t sc = hash32((uint32_t)(v >> (2 * o)) & smask);
+        if (sc < best) {
+          best = sc;
+          j = o;
+        }
+      }
+    }
+    offs |= (uint64_t)j << (5 * c);
+    seedtab_insert(seedtab, seedtab_mask, (uint32_t)(v >> (2 * j)) & smask, 1u << j, n_seeds);
+  }
+  atomicOr(reinterpret_cast<unsigned long long *>(B.toffs + B.slot_of[i]),
+           (unsigned long long)offs << (32 * ori));
+}
+
+// Move the distinct seeds into the right-sized table and set their filter bits.
+__global__ void k_rehash_seeds(const uint64_t *tmp, uint32_t tmp_slots, uint64_t *seedtab,
+                               uint32_t seedtab_mask, uint32_t *bloom, uint32_t seed_mult,
+                               int n_hashes) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= tmp_slots) return;
+  const uint64_t e = tmp[i];
+  if (e == 0) return;
+  const uint32_t x = (uint32_t)e;
+  uint32_t slot = hash32(x) & seedtab_mask;
+  while (atomicCAS(reinterpret_cast<unsigned long long *>(seedtab + slot), 0ull, e) != 0ull)
+    slot = (slot + 1) & seedtab_mask;
+  const uint32_t h = x * seed_mult;
+  uint32_t bits = 0x80000000u >> (x & 31);
+  if (n_hashes == 2) bits |= 0x80000000u >> ((h >> 11) & 31);
+  atomicOr(bloom + __umulhi(h, (uint32_t)BLOOM_WORDS), bits);
+}
+
+// ---- kernel 3: finalise -----------------------------------------------------
+// counts: [3][n]; hits/distinct: [n_variants][2][3]; n_kmers: [n_variants][2]
+__global__ void k_variant_reduce(const uint32_t *counts, const uint32_t *variant,
+                                 const uint8_t *allele, const uint8_t *dead, uint32_t n,
+                                 uint32_t *hits, uint32_t *distinct, uint32_t *n_kmers) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || dead[i]) return;
+  const size_t va = (size_t)variant[i] * 2 + allele[i];
+  atomicAdd(n_kmers + va, 1u);
+#pragma unroll
+  for (int smp = 0; smp < 3; smp++) {
+    const uint32_t c = counts[(size_t)smp * n + i];
+    if (c) {
+      atomicAdd(hits + va * 3 + smp, c);
+      atomicAdd(distinct + va * 3 + smp, 1u);
+    }
+  }
+}
+
+struct Thresholds {
+  uint32_t min_child_alt_hits, min_child_alt_distinct, max_parent_alt_hits, min_parent_ref_hits;
+};
+
+__global__ void k_calls(const uint32_t *hits, const uint32_t *distinct, uint32_t n_variants,
+                        const Thresholds T, uint8_t *calls) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n_variants) return;
+  const uint32_t *h = hits + (size_t)v * 6, *d = distinct + (size_t)v * 6;  // [allele*3+sample]
+  uint8_t c = 0;
+  if (h[3] < T.min_child_alt_hits || d[3] < T.min_child_alt_distinct) c |= 0x02;
+  if (h[4] > T.max_parent_alt_hits) c |= 0x04;
+  if (h[5] > T.max_parent_alt_hits) c |= 0x08;
+  if (h[1] < T.min_parent_ref_hits || h[2] < T.min_parent_ref_hits) c |= 0x10;
+  calls[v] = c ? c : 0x01;
+}
+
+}  // namespace dkb

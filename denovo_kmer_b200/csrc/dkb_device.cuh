@@ -1,0 +1,74 @@
+// dkb_device.cuh — device-side data layout and helpers shared by the build,
+// scan and finalise kernels (sm_100a).  See DESIGN.md §3 for the layout.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dkb {
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+
+// ---- scan geometry -------------------------------------------------------
+constexpr int SCAN_THREADS = 1024;         // one CTA per SM (shared-memory bound)
+constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+constexpr int CHUNK = 64;                  // stream positions per lane per tile (4 words)
+constexpr int WTILE = 32 * CHUNK;          // positions per warp tile (512 B of bases)
+constexpr int WTILE_WORDS = WTILE / 16;    // 128 uint32 words of bases per warp tile
+constexpr int BLOOM_WORDS = 51200;         // 200 KB seed filter resident in shared memory
+constexpr int BQ_CAP = 64;                 // per-warp ring of filter hits (positions)
+constexpr int CQ_CAP = 64;                 // per-warp ring of verified seeds (position, offsets)
+constexpr size_t SCAN_SMEM_BYTES =
+    (size_t)BLOOM_WORDS * 4 + (size_t)SCAN_WARPS * BQ_CAP * 4 + (size_t)SCAN_WARPS * CQ_CAP * 8;
+
+constexpr uint32_t SEED_MULT = 0x9E3779B1u;  // odd multiplier of the filter hash
+constexpr uint64_t KEY_EMPTY = ~0ull;        // keys use at most 62 bits
+constexpr uint32_t ENTRY_DEAD = 0xFFFFFFFFu; // repeated (key, owner) triple
+
+// ---- hashes ----------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x *= 0x85EBCA6Bu;
+  x ^= x >> 15;
+  x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  return x;
+}
+
+__host__ __device__ __forceinline__ uint64_t kmer_mask(int k) { return (1ull << (2 * k)) - 1; }
+
+// Reverse the order of the k bases of a 2k-bit value (an involution).  Turns
+// a key (first base most significant) into stream order (first base least
+// significant) and back.
+__device__ __forceinline__ uint64_t base_reverse(uint64_t v, int k) {
+  uint64_t r = __brevll(v);
+  r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
+  return r >> (64 - 2 * k);
+}
+
+// ---- parameters of one scan launch -------------------------------------------
+struct ScanParams {
+  const uint32_t *bases;  // 2-bit stream, 16 positions per word
+  const uint32_t *mask;   // 1-bit validity stream, 32 positions per word
+  uint32_t n_pos, n_bwords, n_mwords, n_tiles;
+  const uint32_t *bloom;    // BLOOM_WORDS words, copied into shared memory per CTA
+  const uint64_t *seedtab;  // (offset bitmap << 32) | seed, 0 = empty
+  uint32_t seedtab_mask;
+  uint32_t seed_mult;  // SEED_MULT << (32 - 2s): the product ignores bases beyond s
+  uint32_t seed_mask;  // low 2s bits
+  const uint64_t *tkeys;  // canonical key per slot, KEY_EMPTY = empty
+  const uint32_t *tentry; // entry index per slot
+  const uint64_t *toffs;  // designated seed offsets: 5 bits per class, orientation 1 at bit 32
+  uint32_t table_mask;
+  uint32_t *counts;  // this sample's [n_entries] counters
+  int k;
+  unsigned long long *prof;  // 4 counters or nullptr
+};
+
+}  // namespace dkb

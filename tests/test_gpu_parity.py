@@ -1,0 +1,53 @@
+"""-m gpu: the CUDA path through the C ABI against the CPU oracle, bit-exact."""
+import numpy as np
+import pytest
+
+from denovo_kmer_b200 import synth
+from helpers import gpu_counts, oracle_counts
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(dkb, orc, trio, k, min_bq=20, drop_shared=True, **kw):
+    entries = dkb.variant_kmers(trio.variant_tuples(), k, drop_shared=drop_shared)
+    ks, want = oracle_counts(orc, entries, trio, k, min_bq)
+    got, stats, tun = gpu_counts(dkb, entries, trio, k, min_bq, **kw)
+    assert want.max() < 2 ** 32
+    bad = np.nonzero(got.astype(np.uint64) != want)
+    assert len(bad[0]) == 0, (
+        f"tuning={tun} mismatches={len(bad[0])} first={[(int(s), int(e), int(got[s, e]), int(want[s, e])) for s, e in zip(*bad)][:5]}")
+    assert want.sum() > 0
+    return entries, ks, want, got, stats
+
+
+@pytest.mark.parametrize("tuning", [None, (16, 1, 1), (16, 1, 2), (15, 2, 1), (15, 2, 2),
+                                    (14, 4, 1), (14, 4, 2), (12, 1, 1), (9, 2, 1)])
+@pytest.mark.parametrize("hints", [True, False])
+def test_snv_trio_k31(dkb, orc, tuning, hints):
+    trio = synth.make_trio_host(200_000, 12, 40, 31, seed=5)
+    _check(dkb, orc, trio, 31, tuning=tuning, hints=hints)
+
+
+@pytest.mark.parametrize("k", [15, 21, 25, 31, 8, 16, 30])
+def test_k_sweep(dkb, orc, k):
+    trio = synth.make_trio_host(100_000, 10, 20, k, seed=7 + k)
+    _check(dkb, orc, trio, k)
+    _check(dkb, orc, trio, k, hints=False, tuning=(0, 2 if k > 8 else 1, 0))
+
+
+def test_indels_and_shared(dkb, orc):
+    trio = synth.make_trio_host(150_000, 15, 40, 31, seed=11, indel_frac=0.6)
+    _check(dkb, orc, trio, 31)
+    _check(dkb, orc, trio, 31, drop_shared=False)
+    _check(dkb, orc, trio, 31, drop_shared=False, hints=False, tuning=(15, 2, 2))
+
+
+def test_ragged_reads_and_batches(dkb, orc):
+    trio = synth.make_trio_host(100_000, 15, 20, 21, seed=13, ragged=True, n_rate=0.01,
+                                lowq_frac=0.1)
+    _check(dkb, orc, trio, 21, batches=7)
+
+
+def test_no_quality_no_masking(dkb, orc):
+    trio = synth.make_trio_host(100_000, 10, 20, 31, seed=17)
+    _check(dkb, orc, trio, 31, min_bq=0)
