@@ -28,7 +28,8 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "n_entries", "n_live_entries", "table_slots", "n_seeds", "seed_slots", "bloom_words",
         "bloom_bits_set", "scan_launches", "positions_scanned", "bloom_hits", "seed_hits",
-        "windows_probed", "window_hits")] + [("last_scan_ms", C.c_float)]
+        "windows_probed", "window_hits", "scan_launches_timed")] + [
+        ("scan_ms_total", C.c_double), ("last_scan_ms", C.c_float)]
 
 
 # every symbol include/dkb.h declares: (restype, argtypes)

@@ -206,9 +206,17 @@ class KmerCounter:
         self._ck(self._L.dkb_entry_counts_device(self._h, C.byref(p), C.byref(n)))
         return int(p.value or 0), int(n.value)
 
-    def finalise(self, thresholds=DEFAULT_THRESHOLDS):
+    def finalise_launch(self, thresholds=DEFAULT_THRESHOLDS):
+        """Queue kernel 3 on the scan stream without waiting for it."""
         t = Thresholds(*[int(x) for x in thresholds])
         self._ck(self._L.dkb_finalise(self._h, C.byref(t)))
+
+    def finalise(self, thresholds=DEFAULT_THRESHOLDS):
+        """Kernel 3 + fetch: (hits[nv,2,3], distinct[nv,2,3], n_kmers[nv,2], calls[nv])."""
+        self.finalise_launch(thresholds)
+        return self.results()
+
+    def results(self):
         nv = max(self.n_variants, 1)
         hits = np.zeros((nv, 2, 3), dtype=np.uint32)
         dist = np.zeros((nv, 2, 3), dtype=np.uint32)

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/dkb.h"
@@ -52,8 +53,11 @@ struct dkb_ctx {
   unsigned long long *d_prof = nullptr;
   // streams / staging for host batches
   cudaStream_t s_scan = nullptr, s_copy = nullptr;
-  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
-  bool have_timing = false;
+  // per-launch CUDA-event timing of the scan kernel (pooled event pairs)
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool, ev_pending;
+  double scan_ms_total = 0.0;
+  uint64_t scan_launches_timed = 0;
+  float last_scan_ms = 0.f;
   struct Stage {
     uint32_t *bases = nullptr, *mask = nullptr;
     size_t bases_cap = 0, mask_cap = 0;  // in words
@@ -143,6 +147,25 @@ int resolve_tuning(dkb_ctx *ctx, size_t n_entries) {
   return DKB_OK;
 }
 
+// Fold finished scan launches into the running totals; recycle their events.
+void collect_timing(dkb_ctx *ctx) {
+  size_t keep = 0;
+  for (auto &pr : ctx->ev_pending) {
+    float ms = 0.f;
+    if (cudaEventQuery(pr.second) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+      ctx->scan_ms_total += ms;
+      ctx->scan_launches_timed++;
+      ctx->last_scan_ms = ms;
+      ctx->ev_pool.push_back(pr);
+    } else {
+      cudaGetLastError();
+      ctx->ev_pending[keep++] = pr;
+    }
+  }
+  ctx->ev_pending.resize(keep);
+}
+
 typedef void (*scan_fn)(const ScanParams);
 
 scan_fn pick_scan(int D, int NH, bool prof) {
@@ -181,11 +204,20 @@ int launch_scan(dkb_ctx *ctx, const uint32_t *d_bases, const uint32_t *d_mask,
   uint32_t grid = (P.n_tiles + SCAN_WARPS - 1) / SCAN_WARPS;
   if (grid > (uint32_t)ctx->n_sms) grid = ctx->n_sms;
   if (grid == 0) return DKB_OK;
-  CU(cudaEventRecord(ctx->ev_start, ctx->s_scan));
+  if (ctx->ev_pending.size() >= 256) collect_timing(ctx);
+  std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+  if (!ctx->ev_pool.empty()) {
+    ev = ctx->ev_pool.back();
+    ctx->ev_pool.pop_back();
+  } else {
+    CU(cudaEventCreate(&ev.first));
+    CU(cudaEventCreate(&ev.second));
+  }
+  CU(cudaEventRecord(ev.first, ctx->s_scan));
   fn<<<grid, SCAN_THREADS, SCAN_SMEM_BYTES, ctx->s_scan>>>(P);
   CU(cudaGetLastError());
-  CU(cudaEventRecord(ctx->ev_stop, ctx->s_scan));
-  ctx->have_timing = true;
+  CU(cudaEventRecord(ev.second, ctx->s_scan));
+  ctx->ev_pending.push_back(ev);
   ctx->scan_launches++;
   ctx->positions_scanned += n_positions;
   ctx->finalised = false;
@@ -239,8 +271,6 @@ int dkb_ctx_create(int device, int k, dkb_ctx **out) {
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&ctx->s_scan, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking));
-    CU(cudaEventCreate(&ctx->ev_start));
-    CU(cudaEventCreate(&ctx->ev_stop));
     for (auto &st : ctx->stage) {
       CU(cudaEventCreateWithFlags(&st.copied, cudaEventDisableTiming));
       CU(cudaEventCreateWithFlags(&st.freed, cudaEventDisableTiming));
@@ -270,8 +300,11 @@ int dkb_ctx_destroy(dkb_ctx *ctx) {
     if (st.copied) cudaEventDestroy(st.copied);
     if (st.freed) cudaEventDestroy(st.freed);
   }
-  if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
-  if (ctx->ev_stop) cudaEventDestroy(ctx->ev_stop);
+  for (auto *v : {&ctx->ev_pool, &ctx->ev_pending})
+    for (auto &pr : *v) {
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
   if (ctx->s_scan) cudaStreamDestroy(ctx->s_scan);
   if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
   delete ctx;
@@ -548,11 +581,10 @@ int dkb_stats_get(dkb_ctx *ctx, dkb_stats *out) {
   out->seed_hits = prof[1];
   out->windows_probed = prof[2];
   out->window_hits = prof[3];
-  if (ctx->have_timing) {
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_stop) == cudaSuccess) out->last_scan_ms = ms;
-    else cudaGetLastError();
-  }
+  collect_timing(ctx);
+  out->scan_launches_timed = ctx->scan_launches_timed;
+  out->scan_ms_total = ctx->scan_ms_total;
+  out->last_scan_ms = ctx->last_scan_ms;
   return DKB_OK;
 }
 

@@ -165,7 +165,7 @@ struct ScanWarp {
           acc1 = __funnelshift_l(bit, acc1, 1);
       }
     }
-    if (64 / D < 32) acc0 <<= (32 - 64 / D);
+    if constexpr (64 / D < 32) acc0 <<= (32 - 64 / D);
   }
 };
 

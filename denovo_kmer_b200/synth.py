@@ -111,7 +111,10 @@ def sample_reads(haps, n_reads: int, read_len: int, seed: int, err_rate: float =
         if len(idx) == 0:
             continue
         starts = rng.integers(0, len(hap) - read_len + 1, size=len(idx))
-        for r, s in zip(idx, starts):  # small-case generator: a loop is fine
+        if not ragged:  # fixed length: one gather
+            seq.reshape(n_reads, read_len)[idx] = hap[starts[:, None] + np.arange(read_len)[None, :]]
+            continue
+        for r, s in zip(idx, starts):
             seq[int(offsets[r]):int(offsets[r + 1])] = hap[s:s + int(lens[r])]
     # sequencing errors: substitute with a different base
     err = rng.random(total) < err_rate
@@ -120,9 +123,13 @@ def sample_reads(haps, n_reads: int, read_len: int, seed: int, err_rate: float =
         seq[err] = ASCII[(code + rng.integers(1, 4, size=int(err.sum()))) % 4]
     # reverse-complement a fraction of reads (reads from either strand)
     flip = rng.random(n_reads) < rc_frac
-    for r in np.nonzero(flip)[0]:
-        a, b = int(offsets[r]), int(offsets[r + 1])
-        seq[a:b] = COMP_ASCII[seq[a:b][::-1]]
+    if not ragged:
+        m = seq.reshape(n_reads, read_len)
+        m[flip] = COMP_ASCII[m[flip][:, ::-1]]
+    else:
+        for r in np.nonzero(flip)[0]:
+            a, b = int(offsets[r]), int(offsets[r + 1])
+            seq[a:b] = COMP_ASCII[seq[a:b][::-1]]
     seq[rng.random(total) < n_rate] = ord("N")
     qual = rng.integers(25, 41, size=total).astype(np.uint8)
     low = rng.random(total) < lowq_frac

@@ -173,7 +173,9 @@ typedef struct dkb_stats {
   uint64_t scan_launches;    /* scan kernels launched since create */
   uint64_t positions_scanned;
   uint64_t bloom_hits, seed_hits, windows_probed, window_hits; /* if profiling counters on */
-  float last_scan_ms;        /* CUDA-event time of the most recent scan kernel */
+  uint64_t scan_launches_timed; /* launches folded into scan_ms_total */
+  double scan_ms_total;      /* sum of per-launch CUDA-event times of the scan kernel */
+  float last_scan_ms;        /* CUDA-event time of the most recent finished scan kernel */
 } dkb_stats;
 int dkb_stats_get(dkb_ctx *ctx, dkb_stats *out);
 int dkb_profile_counters(dkb_ctx *ctx, int enable);

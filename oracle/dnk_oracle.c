@@ -83,11 +83,16 @@ size_t orc_read_kmers(const uint8_t *seq, const uint8_t *qual, size_t len, int k
 }
 
 /* ---- counter.rs: the k-mer -> owners map -------------------------------- */
+typedef struct orc_slot {
+  uint64_t key; /* valid when ent != ORC_NO_ENTRY */
+  uint32_t ent; /* entry index or ORC_NO_ENTRY for empty */
+  uint32_t pad;
+} orc_slot;
+
 typedef struct orc_set {
   size_t n_entries, cap; /* cap is a power of two */
-  uint64_t *keys;        /* slot key, valid when ent != ORC_NO_ENTRY */
-  uint32_t *ent;         /* slot entry index or ORC_NO_ENTRY for empty */
-  uint8_t *live;         /* [n_entries] 0 for a repeated (key, owner) triple */
+  orc_slot *slots;
+  uint8_t *live; /* [n_entries] 0 for a repeated (key, owner) triple */
 } orc_set;
 
 static inline size_t orc_hash(uint64_t x, size_t cap) {
@@ -107,17 +112,16 @@ orc_set *orc_set_build(const uint64_t *keys, const uint32_t *variant, const uint
   while (cap < 2 * n + 2) cap <<= 1;
   s->n_entries = n;
   s->cap = cap;
-  s->keys = (uint64_t *)malloc(cap * sizeof(uint64_t));
-  s->ent = (uint32_t *)malloc(cap * sizeof(uint32_t));
+  s->slots = (orc_slot *)malloc(cap * sizeof(orc_slot));
   s->live = (uint8_t *)malloc(n ? n : 1);
-  if (!s->keys || !s->ent || !s->live) return NULL;
-  for (size_t i = 0; i < cap; i++) s->ent[i] = ORC_NO_ENTRY;
+  if (!s->slots || !s->live) return NULL;
+  for (size_t i = 0; i < cap; i++) s->slots[i].ent = ORC_NO_ENTRY;
   for (size_t i = 0; i < n; i++) {
     size_t h = orc_hash(keys[i], cap);
     int dup = 0;
-    while (s->ent[h] != ORC_NO_ENTRY) {
-      uint32_t e = s->ent[h];
-      if (s->keys[h] == keys[i] && variant[e] == variant[i] && allele[e] == allele[i]) {
+    while (s->slots[h].ent != ORC_NO_ENTRY) {
+      uint32_t e = s->slots[h].ent;
+      if (s->slots[h].key == keys[i] && variant[e] == variant[i] && allele[e] == allele[i]) {
         dup = 1;
         break;
       }
@@ -125,8 +129,8 @@ orc_set *orc_set_build(const uint64_t *keys, const uint32_t *variant, const uint
     }
     s->live[i] = (uint8_t)!dup;
     if (!dup) {
-      s->keys[h] = keys[i];
-      s->ent[h] = (uint32_t)i;
+      s->slots[h].key = keys[i];
+      s->slots[h].ent = (uint32_t)i;
     }
   }
   return s;
@@ -134,8 +138,7 @@ orc_set *orc_set_build(const uint64_t *keys, const uint32_t *variant, const uint
 
 void orc_set_free(orc_set *s) {
   if (!s) return;
-  free(s->keys);
-  free(s->ent);
+  free(s->slots);
   free(s->live);
   free(s);
 }
@@ -176,8 +179,8 @@ void orc_count_reads(const orc_set *s, const uint8_t *seq, const uint8_t *qual,
         if (++run >= k) {
           uint64_t key = fwd < rc ? fwd : rc;
           size_t h = orc_hash(key, cap);
-          while (s->ent[h] != ORC_NO_ENTRY) {
-            if (s->keys[h] == key) local[s->ent[h]]++;
+          while (s->slots[h].ent != ORC_NO_ENTRY) {
+            if (s->slots[h].key == key) local[s->slots[h].ent]++;
             h = (h + 1) & (cap - 1);
           }
         }

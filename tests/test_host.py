@@ -1,0 +1,138 @@
+"""CPU: the C-ABI library loads and exports every symbol include/dkb.h declares, and its
+host-side pieces (k-mer primitives, read packer, variant k-mer builder) match the oracle.
+No compute entry point is called (no GPU here)."""
+import ctypes as C
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def test_library_exports_every_declared_symbol(dkb):
+    from denovo_kmer_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "dkb.h")).read()
+    declared = set(re.findall(r"\b(dkb_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    L = C.CDLL(_lib.SO_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert _lib.lib().dkb_abi_version() == 1
+
+
+def test_no_cpu_fallback(dkb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(dkb.DkbError) as ei:
+        dkb.KmerCounter(31)
+    assert ei.value.code == 5  # DKB_ENODEV
+
+
+def test_product_does_not_touch_oracle():
+    pkg = os.path.join(ROOT, "denovo_kmer_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.lower() or f == "__never__", f"{f} mentions the oracle"
+
+
+@pytest.mark.parametrize("k", [8, 15, 16, 21, 31])
+def test_kmer_primitives_match_oracle(dkb, orc, k):
+    rnd = random.Random(k)
+    for _ in range(300):
+        s = "".join(rnd.choice("ACGTacgt") for _ in range(k))
+        f = dkb.kmer_encode(s)
+        assert f == orc.py_encode(s.upper())
+        assert dkb.kmer_revcomp(f, k) == orc.revcomp(f, k)
+        assert dkb.kmer_canonical(f, k) == orc.canonical(f, k) == orc.py_canonical_str(s.upper())
+    with pytest.raises(dkb.DkbError):
+        dkb.kmer_encode("ACGN" * 8, k)
+
+
+def _py_pack(reads, min_bq):
+    """Reference packing in plain Python: list of (seq, qual|None) -> (codes, flags)."""
+    codes, flags = [], []
+    for s, q in reads:
+        for i, ch in enumerate(s):
+            c = "ACGT".find(ch.upper())
+            ok = c >= 0 and (q is None or q[i] >= min_bq)
+            codes.append(c if ok else 0)
+            flags.append(1 if ok else 0)
+        codes.append(0)
+        flags.append(0)
+    return codes, flags
+
+
+def test_pack_reads(dkb):
+    rnd = random.Random(4)
+    reads = []
+    for _ in range(200):
+        n = rnd.randint(0, 200)
+        reads.append(("".join(rnd.choice("ACGTNacgtRY") for _ in range(n)),
+                      [rnd.randint(0, 41) for _ in range(n)]))
+    off = np.zeros(len(reads) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(s) for s, _ in reads])
+    seq = np.frombuffer("".join(s for s, _ in reads).encode(), dtype=np.uint8)
+    qual = np.array([x for _, q in reads for x in q], dtype=np.uint8)
+    for min_bq, use_q in ((20, True), (0, True), (20, False)):
+        st = dkb.pack_reads(seq, qual if use_q else None, off, min_bq)
+        codes, flags = _py_pack([(s, q if use_q else None) for s, q in reads], min_bq)
+        assert st.n_positions == len(codes) == int(off[-1]) + len(reads)
+        assert st.n_bases == int(off[-1])
+        p = np.arange(st.n_positions)
+        got_c = (st.bases2[p >> 4] >> (2 * (p & 15)).astype(np.uint32)) & 3
+        got_f = (st.mask1[p >> 5] >> (p & 31).astype(np.uint32)) & 1
+        assert got_c.tolist() == codes and got_f.tolist() == flags
+        bw, mw = dkb.stream_words(st.n_positions)
+        assert len(st.bases2) == bw and len(st.mask1) == mw and bw % 4 == 0 and mw % 4 == 0
+    empty = dkb.pack_reads(np.zeros(0, np.uint8), None, np.zeros(1, np.uint64), 20)
+    assert empty.n_positions == 0
+
+
+@pytest.mark.parametrize("k,indel_frac,drop", [(31, 0.0, True), (21, 0.6, True), (15, 0.6, False),
+                                                (8, 1.0, True)])
+def test_variant_kmers_match_oracle(dkb, orc, k, indel_frac, drop):
+    from denovo_kmer_b200 import synth
+    g = synth.make_genome(30_000, 21)
+    g[100:104] = ord("N")  # an N near the start exercises window skipping
+    vs = synth.plant_variants(g, 60, k, 22, indel_frac=indel_frac)
+    vs.append(synth.Variant(3, "A", "C"))            # left flank shorter than k-1
+    vs.append(synth.Variant(len(g) - 3, "A", "C"))   # right flank shorter than k-1
+    vs.append(synth.Variant(110, chr(g[110]), "T" if chr(g[110]) != "T" else "G"))  # N in flank
+    tup = synth.Trio(k, g, vs).variant_tuples()
+    e = dkb.variant_kmers(tup, k, drop_shared=drop)
+    keys, var, al, wi, wc = orc.variant_entries(tup, k, drop_shared=drop)
+    assert e.keys.tolist() == keys.tolist() and e.variant.tolist() == var.tolist()
+    assert e.allele.tolist() == al.tolist()
+    assert (e.win_index & 0x7FFF).tolist() == wi.tolist() and e.win_count.tolist() == wc.tolist()
+    assert e.n_variants == len(tup) and len(e) > 0
+    # bit 15 of win_index: the haplotype window reads as the reverse complement of the key
+    left, ref, alt, right = tup[0]
+    hap = left[-(k - 1):] + ref + right[: k - 1]
+    m = (e.variant == 0) & (e.allele == 0)
+    for key, w in zip(e.keys[m].tolist(), e.win_index[m].tolist()):
+        lo = max(0, len(left[-(k - 1):]) - k + 1)
+        fwd = orc.py_encode(hap[lo + (w & 0x7FFF): lo + (w & 0x7FFF) + k])
+        assert (fwd != key) == bool(w & 0x8000)
+
+
+def test_argument_validation(dkb):
+    from denovo_kmer_b200 import _lib
+    L = _lib.lib()
+    h = C.c_void_p()
+    assert L.dkb_ctx_create(0, 32, C.byref(h)) == _lib.EINVAL
+    assert L.dkb_ctx_create(0, 7, C.byref(h)) == _lib.EINVAL
+    assert L.dkb_ctx_create(0, 31, None) == _lib.EINVAL
+    assert L.dkb_sync(None) == _lib.EINVAL and L.dkb_ctx_destroy(None) == _lib.OK
+    assert L.dkb_strerror(_lib.ENODEV).decode().startswith("no usable CUDA device")
+    n = C.c_size_t(0)
+    arr = (C.c_char_p * 1)(b"A")
+    assert L.dkb_variant_kmers(arr, arr, arr, arr, 1, 40, 1, None, None, None, None, None,
+                               C.byref(n)) == _lib.EINVAL
