@@ -93,6 +93,12 @@ uint32_t pow2_at_least(uint64_t x) {
   return p;
 }
 
+uint32_t log2_u32(uint32_t pow2) {
+  uint32_t l = 0;
+  while ((1u << l) < pow2) l++;
+  return l;
+}
+
 template <typename T>
 void dfree(T *&p) {
   if (p) cudaFree(p);
@@ -137,10 +143,9 @@ int resolve_tuning(dkb_ctx *ctx, size_t n_entries) {
   if (NH == 0) {
     // two bits per seed pay once the filter holds more than ~1 seed per 50 bits
     const double est_seeds = (double)n_entries * 0.25 * D;
-    NH = (s >= 11 && est_seeds > BLOOM_WORDS * 32 / 50.0) ? 2 : 1;
+    NH = est_seeds > BLOOM_WORDS * 32 / 50.0 ? 2 : 1;
   }
   if (NH != 1 && NH != 2) return fail(ctx, DKB_EINVAL, "bloom_hashes must be 1 or 2");
-  if (NH == 2 && s < 11) return fail(ctx, DKB_EINVAL, "bloom_hashes=2 needs seed_len >= 11");
   ctx->s = s;
   ctx->D = D;
   ctx->NH = NH;
@@ -188,8 +193,10 @@ int launch_scan(dkb_ctx *ctx, const uint32_t *d_bases, const uint32_t *d_mask,
   P.bloom = ctx->d_bloom;
   P.seedtab = ctx->d_seedtab;
   P.seedtab_mask = ctx->seed_slots - 1;
+  P.seedtab_shift = 32 - log2_u32(ctx->seed_slots);
   P.seed_mult = ctx->s == 16 ? SEED_MULT : SEED_MULT << (32 - 2 * ctx->s);
   P.seed_mask = ctx->s == 16 ? 0xFFFFFFFFu : ((1u << (2 * ctx->s)) - 1);
+  P.four = 4;
   P.tkeys = ctx->d_tkeys;
   P.tentry = ctx->d_tentry;
   P.toffs = ctx->d_toffs;
@@ -408,7 +415,7 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
       k_insert_entries<<<g1, TB, 0, st>>>(B);
       k_mark_repeats<<<g1, TB, 0, st>>>(B);
       k_apply_dead<<<g1, TB, 0, st>>>(B);
-      k_assign_seeds<<<g2, TB, 0, st>>>(B, d_tmp, tmp_slots - 1, d_nseeds);
+      k_assign_seeds<<<g2, TB, 0, st>>>(B, d_tmp, tmp_slots - 1, 32 - log2_u32(tmp_slots), d_nseeds);
       CU(cudaGetLastError());
     }
     unsigned int n_seeds = 0;
@@ -420,7 +427,8 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
     CU(cudaMemsetAsync(ctx->d_seedtab, 0, (size_t)ctx->seed_slots * 8, st));
     const uint32_t seed_mult = ctx->s == 16 ? SEED_MULT : SEED_MULT << (32 - 2 * ctx->s);
     k_rehash_seeds<<<(tmp_slots + TB - 1) / TB, TB, 0, st>>>(
-        d_tmp, tmp_slots, ctx->d_seedtab, ctx->seed_slots - 1, ctx->d_bloom, seed_mult, ctx->NH);
+        d_tmp, tmp_slots, ctx->d_seedtab, ctx->seed_slots - 1, 32 - log2_u32(ctx->seed_slots),
+        ctx->d_bloom, seed_mult, ctx->NH);
     CU(cudaGetLastError());
     std::vector<uint32_t> bloom(BLOOM_WORDS);
     std::vector<uint8_t> dead(n1);

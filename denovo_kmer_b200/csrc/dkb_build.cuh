@@ -70,9 +70,10 @@ __global__ void k_apply_dead(const BuildParams B) {
 }
 
 // Insert (seed, offset bit) into an exact seed table; *n_new counts distinct seeds.
-__device__ __forceinline__ void seedtab_insert(uint64_t *tab, uint32_t mask, uint32_t seed,
-                                               uint32_t info, unsigned int *n_new) {
-  uint32_t slot = hash32(seed) & mask;
+__device__ __forceinline__ void seedtab_insert(uint64_t *tab, uint32_t mask, uint32_t shift,
+                                               uint32_t seed, uint32_t info,
+                                               unsigned int *n_new) {
+  uint32_t slot = seed_slot(seed, shift);
   const unsigned long long word = (unsigned long long)info << 32 | seed;
   while (true) {
     unsigned long long old = tab[slot];
@@ -99,7 +100,7 @@ __device__ __forceinline__ void seedtab_insert(uint64_t *tab, uint32_t mask, uin
 //     them (2 seeds per SNV haplotype strand at k=31, s=16, D=1);
 //   min-hash rule (no hints): the s-mer of the class with the smallest hash.
 __global__ void k_assign_seeds(const BuildParams B, uint64_t *seedtab, uint32_t seedtab_mask,
-                               unsigned int *n_seeds) {
+                               uint32_t seedtab_shift, unsigned int *n_seeds) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t i = t >> 1;
   const int ori = t & 1;
@@ -143,7 +144,8 @@ __global__ void k_assign_seeds(const BuildParams B, uint64_t *seedtab, uint32_t 
       }
     }
     offs |= (uint64_t)j << (5 * c);
-    seedtab_insert(seedtab, seedtab_mask, (uint32_t)(v >> (2 * j)) & smask, 1u << j, n_seeds);
+    seedtab_insert(seedtab, seedtab_mask, seedtab_shift, (uint32_t)(v >> (2 * j)) & smask, 1u << j,
+                   n_seeds);
   }
   atomicOr(reinterpret_cast<unsigned long long *>(B.toffs + B.slot_of[i]),
            (unsigned long long)offs << (32 * ori));
@@ -151,19 +153,19 @@ __global__ void k_assign_seeds(const BuildParams B, uint64_t *seedtab, uint32_t 
 
 // Move the distinct seeds into the right-sized table and set their filter bits.
 __global__ void k_rehash_seeds(const uint64_t *tmp, uint32_t tmp_slots, uint64_t *seedtab,
-                               uint32_t seedtab_mask, uint32_t *bloom, uint32_t seed_mult,
-                               int n_hashes) {
+                               uint32_t seedtab_mask, uint32_t seedtab_shift, uint32_t *bloom,
+                               uint32_t seed_mult, int n_hashes) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= tmp_slots) return;
   const uint64_t e = tmp[i];
   if (e == 0) return;
   const uint32_t x = (uint32_t)e;
-  uint32_t slot = hash32(x) & seedtab_mask;
+  uint32_t slot = seed_slot(x, seedtab_shift);
   while (atomicCAS(reinterpret_cast<unsigned long long *>(seedtab + slot), 0ull, e) != 0ull)
     slot = (slot + 1) & seedtab_mask;
   const uint32_t h = x * seed_mult;
-  uint32_t bits = 0x80000000u >> (x & 31);
-  if (n_hashes == 2) bits |= 0x80000000u >> ((h >> 11) & 31);
+  uint32_t bits = bloom_bit1(x);
+  if (n_hashes == 2) bits |= bloom_bit2(h);
   atomicOr(bloom + __umulhi(h, (uint32_t)BLOOM_WORDS), bits);
 }
 

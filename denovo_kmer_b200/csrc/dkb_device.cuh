@@ -14,13 +14,15 @@ constexpr int SCAN_WARPS = SCAN_THREADS / 32;
 constexpr int CHUNK = 64;                  // stream positions per lane per tile (4 words)
 constexpr int WTILE = 32 * CHUNK;          // positions per warp tile (512 B of bases)
 constexpr int WTILE_WORDS = WTILE / 16;    // 128 uint32 words of bases per warp tile
-constexpr int BLOOM_WORDS = 51200;         // 200 KB seed filter resident in shared memory
-constexpr int BQ_CAP = 64;                 // per-warp ring of filter hits (positions)
+constexpr int BLOOM_WORDS = 52736;         // 206 KB seed filter resident in shared memory
+constexpr int HL_CAP = 64;                 // per-warp ring of filter-hit ids (lane << 6 | lookup)
 constexpr int CQ_CAP = 64;                 // per-warp ring of verified seeds (position, offsets)
 constexpr size_t SCAN_SMEM_BYTES =
-    (size_t)BLOOM_WORDS * 4 + (size_t)SCAN_WARPS * BQ_CAP * 4 + (size_t)SCAN_WARPS * CQ_CAP * 8;
+    (size_t)BLOOM_WORDS * 4 + (size_t)SCAN_WARPS * CQ_CAP * 8 + (size_t)SCAN_WARPS * HL_CAP * 2;
 
 constexpr uint32_t SEED_MULT = 0x9E3779B1u;  // odd multiplier of the filter hash
+constexpr uint32_t SEED_MULT2 = 0x85EBCA77u; // second filter bit: bits 32..36 of hash * SEED_MULT2
+constexpr uint32_t SEEDTAB_MULT = 0xC2B2AE3Du; // seed table slot = (seed * SEEDTAB_MULT) >> shift
 constexpr uint64_t KEY_EMPTY = ~0ull;        // keys use at most 62 bits
 constexpr uint32_t ENTRY_DEAD = 0xFFFFFFFFu; // repeated (key, owner) triple
 
@@ -39,6 +41,19 @@ __host__ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
   x *= 0xC2B2AE35u;
   x ^= x >> 16;
   return x;
+}
+
+// slot of a seed in the exact seed table (multiplicative hash, top bits)
+__host__ __device__ __forceinline__ uint32_t seed_slot(uint32_t seed, uint32_t shift) {
+  return (seed * SEEDTAB_MULT) >> shift;
+}
+
+// the two filter bits of a seed whose filter hash is h (bit 31 = index 0)
+__host__ __device__ __forceinline__ uint32_t bloom_bit1(uint32_t seed) {
+  return 0x80000000u >> (seed & 31);
+}
+__host__ __device__ __forceinline__ uint32_t bloom_bit2(uint32_t h) {
+  return 0x80000000u >> ((uint32_t)(((uint64_t)h * SEED_MULT2) >> 32) & 31);
 }
 
 __host__ __device__ __forceinline__ uint64_t kmer_mask(int k) { return (1ull << (2 * k)) - 1; }
@@ -60,8 +75,10 @@ struct ScanParams {
   const uint32_t *bloom;    // BLOOM_WORDS words, copied into shared memory per CTA
   const uint64_t *seedtab;  // (offset bitmap << 32) | seed, 0 = empty
   uint32_t seedtab_mask;
+  uint32_t seedtab_shift;  // 32 - log2(slots)
   uint32_t seed_mult;  // SEED_MULT << (32 - 2s): the product ignores bases beyond s
   uint32_t seed_mask;  // low 2s bits
+  uint32_t four;       // = 4, opaque to the compiler: keeps the filter address on the FMA pipe
   const uint64_t *tkeys;  // canonical key per slot, KEY_EMPTY = empty
   const uint32_t *tentry; // entry index per slot
   const uint64_t *toffs;  // designated seed offsets: 5 bits per class, orientation 1 at bit 32

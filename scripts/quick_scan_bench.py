@@ -38,7 +38,7 @@ for tun in tunings:
             if not prof:
                 best = min(ms[1:])
                 print(json.dumps(dict(tuning=tun, hints=hints, ms=round(best,3), gpos_s=round(n_pos/best/1e6,1),
-                      n_entries=st0['n_entries'], n_seeds=st0['n_seeds'], bloom_density=round(st0['bloom_bits_set']/(51200*32),4))))
+                      n_entries=st0['n_entries'], n_seeds=st0['n_seeds'], bloom_density=round(st0['bloom_bits_set']/(st0['bloom_words']*32),4))))
             else:
                 lookups = n_pos / tun[1]
                 print('   prof ms=%.3f bloom_hit_rate=%.4f seed_hits=%d windows=%d hits=%d' % (min(ms[1:]), s['bloom_hits']/lookups, s['seed_hits'], s['windows_probed'], s['window_hits']))
