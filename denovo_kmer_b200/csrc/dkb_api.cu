@@ -38,7 +38,7 @@ struct dkb_ctx {
   uint64_t *d_toffs = nullptr;
   uint32_t table_slots = 0;
   // seeds
-  uint64_t *d_seedtab = nullptr;
+  uint32_t *d_seeds = nullptr, *d_sinfo = nullptr;
   uint32_t seed_slots = 0;
   uint32_t n_seeds = 0;
   uint32_t *d_bloom = nullptr;
@@ -108,7 +108,7 @@ void dfree(T *&p) {
 void free_table(dkb_ctx *c) {
   dfree(c->d_keys); dfree(c->d_variant); dfree(c->d_allele); dfree(c->d_dead);
   dfree(c->d_tkeys); dfree(c->d_tentry); dfree(c->d_toffs);
-  dfree(c->d_seedtab); dfree(c->d_bloom);
+  dfree(c->d_seeds); dfree(c->d_sinfo); dfree(c->d_bloom);
   dfree(c->d_counts); dfree(c->d_hits); dfree(c->d_distinct); dfree(c->d_nkmers);
   dfree(c->d_calls);
   c->n_entries = c->n_live = 0;
@@ -133,12 +133,13 @@ int resolve_tuning(dkb_ctx *ctx, size_t n_entries) {
   if (D != 1 && D != 2 && D != 4) return fail(ctx, DKB_EINVAL, "stride must be 1, 2 or 4");
   int s = t.seed_len;
   if (s == 0) {
-    s = k - D + 1 < 16 ? k - D + 1 : 16;
-    // keep a ladder of exactly two seeds per strand possible: spacing floor((k-s+1)/D)*D
+    s = k - D + 1 < MAX_SEED_LEN ? k - D + 1 : MAX_SEED_LEN;
+    // keep a ladder of exactly two seeds per strand and class possible for SNVs:
+    // spacing floor((k-s+1)/D)*D must reach 16 at k = 31
     if (D == 4 && s > 14 && k - 14 + 1 >= 16) s = 14;
-    if (D == 2 && s > 15 && k - 15 + 1 >= 16) s = 15;
   }
-  if (s < 8 || s > 16 || s > k - D + 1) return fail(ctx, DKB_EINVAL, "seed_len out of range");
+  if (s < 8 || s > MAX_SEED_LEN || s > k - D + 1)
+    return fail(ctx, DKB_EINVAL, "seed_len out of range (8..15 and <= k - stride + 1)");
   int NH = t.bloom_hashes;
   if (NH == 0) {
     // two bits per seed pay once the filter holds more than ~1 seed per 50 bits
@@ -171,6 +172,24 @@ void collect_timing(dkb_ctx *ctx) {
   ctx->ev_pending.resize(keep);
 }
 
+SeedTable seed_table(const dkb_ctx *ctx) {
+  SeedTable T;
+  T.seeds = ctx->d_seeds;
+  T.sinfo = ctx->d_sinfo;
+  T.bucket_mask = ctx->seed_slots / BUCKET - 1;
+  T.shift = 32 - log2_u32(ctx->seed_slots / BUCKET);
+  return T;
+}
+
+KeyTable key_table(const dkb_ctx *ctx) {
+  KeyTable T;
+  T.keys = ctx->d_tkeys;
+  T.entry = ctx->d_tentry;
+  T.offs = ctx->d_toffs;
+  T.bucket_mask = ctx->table_slots / BUCKET - 1;
+  return T;
+}
+
 typedef void (*scan_fn)(const ScanParams);
 
 scan_fn pick_scan(int D, int NH, bool prof) {
@@ -191,18 +210,14 @@ int launch_scan(dkb_ctx *ctx, const uint32_t *d_bases, const uint32_t *d_mask,
   P.n_mwords = (uint32_t)dkb_stream_mask_words(n_positions);
   P.n_tiles = (uint32_t)((n_positions + WTILE - 1) / WTILE);
   P.bloom = ctx->d_bloom;
-  P.seedtab = ctx->d_seedtab;
-  P.seedtab_mask = ctx->seed_slots - 1;
-  P.seedtab_shift = 32 - log2_u32(ctx->seed_slots);
-  P.seed_mult = ctx->s == 16 ? SEED_MULT : SEED_MULT << (32 - 2 * ctx->s);
-  P.seed_mask = ctx->s == 16 ? 0xFFFFFFFFu : ((1u << (2 * ctx->s)) - 1);
+  P.st = seed_table(ctx);
+  P.kt = key_table(ctx);
+  P.seed_mult = SEED_MULT << (32 - 2 * ctx->s);
+  P.seed_mask = (1u << (2 * ctx->s)) - 1;
   P.four = 4;
-  P.tkeys = ctx->d_tkeys;
-  P.tentry = ctx->d_tentry;
-  P.toffs = ctx->d_toffs;
-  P.table_mask = ctx->table_slots - 1;
   P.counts = ctx->d_counts + (size_t)sample * ctx->n_entries;
   P.k = ctx->k;
+  P.s = ctx->s;
   P.prof = ctx->d_prof;
   scan_fn fn = pick_scan(ctx->D, ctx->NH, ctx->prof);
   if (!fn) return fail(ctx, DKB_EINVAL, "no scan kernel for this tuning");
@@ -358,13 +373,13 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
   ctx->n_entries = n;
   ctx->n_variants = n_variants;
   const size_t n1 = n ? n : 1, nv1 = n_variants ? n_variants : 1;
-  ctx->table_slots = pow2_at_least(2 * (uint64_t)n + 2);
+  ctx->table_slots = pow2_at_least(4 * (uint64_t)n + 2);  // <= 1 entry per 4-slot bucket on average
   uint16_t *d_wi = nullptr, *d_wc = nullptr;
   uint32_t *d_slot_of = nullptr;
-  uint64_t *d_tmp = nullptr;
+  uint32_t *d_set = nullptr;
   unsigned int *d_nseeds = nullptr;
   cudaStream_t st = ctx->s_scan;
-  auto cleanup = [&]() { dfree(d_wi); dfree(d_wc); dfree(d_slot_of); dfree(d_tmp); dfree(d_nseeds); };
+  auto cleanup = [&]() { dfree(d_wi); dfree(d_wc); dfree(d_slot_of); dfree(d_set); dfree(d_nseeds); };
   rc = [&]() -> int {
     CU(cudaMalloc(&ctx->d_keys, n1 * 8));
     CU(cudaMalloc(&ctx->d_variant, n1 * 4));
@@ -399,37 +414,41 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
         CU(cudaMemcpyAsync(d_wc, win_count, n * 2, cudaMemcpyHostToDevice, st));
       }
     }
-    // seeds: first into an over-sized table, then re-hashed into a right-sized one
-    const uint32_t tmp_slots = pow2_at_least(4 * (uint64_t)n * ctx->D + 2);
-    CU(cudaMalloc(&d_tmp, (size_t)tmp_slots * 8));
-    CU(cudaMemsetAsync(d_tmp, 0, (size_t)tmp_slots * 8, st));
+    // sizing pass: count the distinct seeds in a plain open-addressing set
+    const uint32_t set_slots = pow2_at_least(4 * (uint64_t)n * ctx->D + 2);
+    CU(cudaMalloc(&d_set, (size_t)set_slots * 4));
+    CU(cudaMemsetAsync(d_set, 0xFF, (size_t)set_slots * 4, st));
     BuildParams B;
     B.keys = ctx->d_keys; B.variant = ctx->d_variant; B.allele = ctx->d_allele;
     B.win_index = d_wi; B.win_count = d_wc; B.n = (uint32_t)n;
-    B.tkeys = ctx->d_tkeys; B.tentry = ctx->d_tentry; B.toffs = ctx->d_toffs;
-    B.table_mask = ctx->table_slots - 1; B.slot_of = d_slot_of; B.dead = ctx->d_dead;
+    B.kt = key_table(ctx); B.slot_of = d_slot_of; B.dead = ctx->d_dead;
     B.k = ctx->k; B.s = ctx->s; B.D = ctx->D;
+    const uint32_t seed_mult = SEED_MULT << (32 - 2 * ctx->s);
     const int TB = 256;
+    const uint32_t g1 = (uint32_t)((n + TB - 1) / TB), g2 = (uint32_t)((2 * n + TB - 1) / TB);
     if (n) {
-      const uint32_t g1 = (uint32_t)((n + TB - 1) / TB), g2 = (uint32_t)((2 * n + TB - 1) / TB);
       k_insert_entries<<<g1, TB, 0, st>>>(B);
       k_mark_repeats<<<g1, TB, 0, st>>>(B);
       k_apply_dead<<<g1, TB, 0, st>>>(B);
-      k_assign_seeds<<<g2, TB, 0, st>>>(B, d_tmp, tmp_slots - 1, 32 - log2_u32(tmp_slots), d_nseeds);
+      k_assign_seeds<<<g2, TB, 0, st>>>(B, true, d_set, set_slots - 1, d_nseeds, SeedTable{},
+                                        nullptr, seed_mult, ctx->NH);
       CU(cudaGetLastError());
     }
     unsigned int n_seeds = 0;
     CU(cudaMemcpyAsync(&n_seeds, d_nseeds, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     ctx->n_seeds = n_seeds;
-    ctx->seed_slots = pow2_at_least(3 * (uint64_t)n_seeds + 2);
-    CU(cudaMalloc(&ctx->d_seedtab, (size_t)ctx->seed_slots * 8));
-    CU(cudaMemsetAsync(ctx->d_seedtab, 0, (size_t)ctx->seed_slots * 8, st));
-    const uint32_t seed_mult = ctx->s == 16 ? SEED_MULT : SEED_MULT << (32 - 2 * ctx->s);
-    k_rehash_seeds<<<(tmp_slots + TB - 1) / TB, TB, 0, st>>>(
-        d_tmp, tmp_slots, ctx->d_seedtab, ctx->seed_slots - 1, 32 - log2_u32(ctx->seed_slots),
-        ctx->d_bloom, seed_mult, ctx->NH);
-    CU(cudaGetLastError());
+    // <= 0.5 seeds per 4-slot bucket on average: a full bucket (second load) is a 1-in-600 event
+    ctx->seed_slots = pow2_at_least(8 * (uint64_t)n_seeds + 2);
+    CU(cudaMalloc(&ctx->d_seeds, (size_t)ctx->seed_slots * 4));
+    CU(cudaMalloc(&ctx->d_sinfo, (size_t)ctx->seed_slots * 4));
+    CU(cudaMemsetAsync(ctx->d_seeds, 0xFF, (size_t)ctx->seed_slots * 4, st));
+    CU(cudaMemsetAsync(ctx->d_sinfo, 0, (size_t)ctx->seed_slots * 4, st));
+    if (n) {
+      k_assign_seeds<<<g2, TB, 0, st>>>(B, false, nullptr, 0, nullptr, seed_table(ctx),
+                                        ctx->d_bloom, seed_mult, ctx->NH);
+      CU(cudaGetLastError());
+    }
     std::vector<uint32_t> bloom(BLOOM_WORDS);
     std::vector<uint8_t> dead(n1);
     CU(cudaMemcpyAsync(bloom.data(), ctx->d_bloom, (size_t)BLOOM_WORDS * 4, cudaMemcpyDeviceToHost, st));

@@ -2,9 +2,9 @@
 //
 // Build = the GPU form of src/counter.rs's "set of k-mers that span each
 // candidate allele" (unmounted): every entry (canonical key,
-// variant, allele) gets a slot in an open-addressing multimap; for both
-// orientations of the key and every stride class one s-mer of the k-mer is
-// designated as its seed and put in the exact seed table and the filter.
+// variant, allele) gets a slot in a bucketised open-addressing multimap; for
+// both orientations of the key and every stride class one s-mer of the k-mer
+// is designated as its seed and put in the exact seed table and the filter.
 #pragma once
 #include "dkb_device.cuh"
 
@@ -17,28 +17,31 @@ struct BuildParams {
   const uint16_t *win_index;  // may be null: bit 15 = haplotype window is the rc of the key
   const uint16_t *win_count;  // may be null
   uint32_t n;
-  uint64_t *tkeys;
-  uint32_t *tentry;
-  uint64_t *toffs;
-  uint32_t table_mask;
+  KeyTable kt;
   uint32_t *slot_of;  // [n] slot claimed by each entry
   uint8_t *dead;      // [n]
   int k, s, D;
 };
 
+// Claim one free slot for every entry: home bucket first, then the following
+// buckets.  A multimap: equal keys take separate slots.
 __global__ void k_insert_entries(const BuildParams B) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B.n) return;
   const uint64_t key = B.keys[i];
-  uint32_t slot = (uint32_t)mix64(key) & B.table_mask;
+  uint32_t b = key_bucket(key, B.kt.bucket_mask);
   while (true) {
-    const unsigned long long old =
-        atomicCAS(reinterpret_cast<unsigned long long *>(B.tkeys + slot), KEY_EMPTY, key);
-    if (old == KEY_EMPTY) break;
-    slot = (slot + 1) & B.table_mask;
+    for (int j = 0; j < BUCKET; j++) {
+      const uint32_t slot = b * BUCKET + j;
+      if (atomicCAS(reinterpret_cast<unsigned long long *>(B.kt.keys + slot), KEY_EMPTY, key) ==
+          KEY_EMPTY) {
+        B.kt.entry[slot] = i;
+        B.slot_of[i] = slot;
+        return;
+      }
+    }
+    b = (b + 1) & B.kt.bucket_mask;
   }
-  B.tentry[slot] = i;
-  B.slot_of[i] = slot;
 }
 
 // An entry is dead when an earlier entry has the same (key, variant, allele).
@@ -46,19 +49,21 @@ __global__ void k_mark_repeats(const BuildParams B) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B.n) return;
   const uint64_t key = B.keys[i];
-  uint32_t slot = (uint32_t)mix64(key) & B.table_mask;
+  uint32_t b = key_bucket(key, B.kt.bucket_mask);
   uint8_t dead = 0;
-  while (true) {
-    const uint64_t tk = B.tkeys[slot];
-    if (tk == KEY_EMPTY) break;
-    if (tk == key) {
-      const uint32_t e = B.tentry[slot];
-      if (e < i && B.variant[e] == B.variant[i] && B.allele[e] == B.allele[i]) {
-        dead = 1;
-        break;
+  bool open = false;
+  while (!open && !dead) {
+    for (int j = 0; j < BUCKET; j++) {
+      const uint32_t slot = b * BUCKET + j;
+      const uint64_t tk = B.kt.keys[slot];
+      if (tk == KEY_EMPTY) {
+        open = true;
+      } else if (tk == key) {
+        const uint32_t e = B.kt.entry[slot];
+        if (e < i && B.variant[e] == B.variant[i] && B.allele[e] == B.allele[i]) dead = 1;
       }
     }
-    slot = (slot + 1) & B.table_mask;
+    b = (b + 1) & B.kt.bucket_mask;
   }
   B.dead[i] = dead;
 }
@@ -66,41 +71,53 @@ __global__ void k_mark_repeats(const BuildParams B) {
 __global__ void k_apply_dead(const BuildParams B) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B.n) return;
-  if (B.dead[i]) B.tentry[B.slot_of[i]] = ENTRY_DEAD;
+  if (B.dead[i]) B.kt.entry[B.slot_of[i]] = ENTRY_DEAD;
 }
 
-// Insert (seed, offset bit) into an exact seed table; *n_new counts distinct seeds.
-__device__ __forceinline__ void seedtab_insert(uint64_t *tab, uint32_t mask, uint32_t shift,
-                                               uint32_t seed, uint32_t info,
-                                               unsigned int *n_new) {
-  uint32_t slot = seed_slot(seed, shift);
-  const unsigned long long word = (unsigned long long)info << 32 | seed;
+// Insert (seed, offset bit) into the bucketised seed table.
+__device__ __forceinline__ void seedtab_insert(const SeedTable &T, uint32_t seed, uint32_t info) {
+  uint32_t b = seed_bucket(seed, T.shift);
   while (true) {
-    unsigned long long old = tab[slot];
-    if (old == 0) {
-      old = atomicCAS(reinterpret_cast<unsigned long long *>(tab + slot), 0ull, word);
-      if (old == 0) {
-        if (n_new) atomicAdd(n_new, 1u);
+    for (int j = 0; j < BUCKET; j++) {
+      const uint32_t slot = b * BUCKET + j;
+      uint32_t old = T.seeds[slot];
+      if (old == SEED_EMPTY) old = atomicCAS(T.seeds + slot, SEED_EMPTY, seed);
+      if (old == SEED_EMPTY || old == seed) {
+        atomicOr(T.sinfo + slot, info);
         return;
       }
     }
-    if ((uint32_t)old == seed) {
-      atomicOr(reinterpret_cast<unsigned long long *>(tab + slot),
-               (unsigned long long)info << 32);
+    b = (b + 1) & T.bucket_mask;
+  }
+}
+
+// Count distinct seeds with a plain open-addressing set (sizing pass).
+__device__ __forceinline__ void seedset_insert(uint32_t *set, uint32_t mask, uint32_t seed,
+                                               unsigned int *n_new) {
+  uint32_t slot = hash32(seed) & mask;
+  while (true) {
+    uint32_t old = set[slot];
+    if (old == SEED_EMPTY) old = atomicCAS(set + slot, SEED_EMPTY, seed);
+    if (old == SEED_EMPTY) {
+      atomicAdd(n_new, 1u);
       return;
     }
+    if (old == seed) return;
     slot = (slot + 1) & mask;
   }
 }
 
 // One thread per (entry, orientation): choose the designated seed offset of
-// every stride class, record it in the slot and register the seed.
+// every stride class.
 //   ladder rule (window hints present): seeds sit on a ladder of spacing
 //     G = floor((k-s+1)/D)*D along the haplotype, so neighbouring windows share
-//     them (2 seeds per SNV haplotype strand at k=31, s=16, D=1);
+//     them (2 seeds per SNV haplotype strand and class at k=31, s<=15);
 //   min-hash rule (no hints): the s-mer of the class with the smallest hash.
-__global__ void k_assign_seeds(const BuildParams B, uint64_t *seedtab, uint32_t seedtab_mask,
-                               uint32_t seedtab_shift, unsigned int *n_seeds) {
+// count_only: just add the seeds to `set` (sizing pass); otherwise record the
+// offsets in the entry's slot, insert the seeds and set their filter bits.
+__global__ void k_assign_seeds(const BuildParams B, bool count_only, uint32_t *set,
+                               uint32_t set_mask, unsigned int *n_seeds, const SeedTable T,
+                               uint32_t *bloom, uint32_t seed_mult, int n_hashes) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t i = t >> 1;
   const int ori = t & 1;
@@ -112,7 +129,7 @@ __global__ void k_assign_seeds(const BuildParams B, uint64_t *seedtab, uint32_t 
   const uint64_t v1 = ~key & km;             // stream order of its reverse complement
   if (ori == 1 && v1 == v0) return;          // palindrome: one orientation only
   const uint64_t v = ori ? v1 : v0;
-  const uint32_t smask = s == 16 ? 0xFFFFFFFFu : ((1u << (2 * s)) - 1);
+  const uint32_t smask = (1u << (2 * s)) - 1;
   const bool ladder = B.win_index != nullptr && B.win_count != nullptr;
   uint32_t u = 0;
   if (ladder) {
@@ -143,30 +160,21 @@ __global__ void k_assign_seeds(const BuildParams B, uint64_t *seedtab, uint32_t 
         }
       }
     }
-    offs |= (uint64_t)j << (5 * c);
-    seedtab_insert(seedtab, seedtab_mask, seedtab_shift, (uint32_t)(v >> (2 * j)) & smask, 1u << j,
-                   n_seeds);
+    const uint32_t seed = (uint32_t)(v >> (2 * j)) & smask;
+    if (count_only) {
+      seedset_insert(set, set_mask, seed, n_seeds);
+    } else {
+      offs |= (uint64_t)j << (5 * c);
+      seedtab_insert(T, seed, 1u << j);
+      const uint32_t h = seed * seed_mult;
+      uint32_t bits = bloom_bit1(seed);
+      if (n_hashes == 2) bits |= bloom_bit2(h);
+      atomicOr(bloom + __umulhi(h, (uint32_t)BLOOM_WORDS), bits);
+    }
   }
-  atomicOr(reinterpret_cast<unsigned long long *>(B.toffs + B.slot_of[i]),
-           (unsigned long long)offs << (32 * ori));
-}
-
-// Move the distinct seeds into the right-sized table and set their filter bits.
-__global__ void k_rehash_seeds(const uint64_t *tmp, uint32_t tmp_slots, uint64_t *seedtab,
-                               uint32_t seedtab_mask, uint32_t seedtab_shift, uint32_t *bloom,
-                               uint32_t seed_mult, int n_hashes) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= tmp_slots) return;
-  const uint64_t e = tmp[i];
-  if (e == 0) return;
-  const uint32_t x = (uint32_t)e;
-  uint32_t slot = seed_slot(x, seedtab_shift);
-  while (atomicCAS(reinterpret_cast<unsigned long long *>(seedtab + slot), 0ull, e) != 0ull)
-    slot = (slot + 1) & seedtab_mask;
-  const uint32_t h = x * seed_mult;
-  uint32_t bits = bloom_bit1(x);
-  if (n_hashes == 2) bits |= bloom_bit2(h);
-  atomicOr(bloom + __umulhi(h, (uint32_t)BLOOM_WORDS), bits);
+  if (!count_only)
+    atomicOr(reinterpret_cast<unsigned long long *>(B.kt.offs + B.slot_of[i]),
+             (unsigned long long)offs << (32 * ori));
 }
 
 // ---- kernel 3: finalise -----------------------------------------------------

@@ -14,17 +14,20 @@ constexpr int SCAN_WARPS = SCAN_THREADS / 32;
 constexpr int CHUNK = 64;                  // stream positions per lane per tile (4 words)
 constexpr int WTILE = 32 * CHUNK;          // positions per warp tile (512 B of bases)
 constexpr int WTILE_WORDS = WTILE / 16;    // 128 uint32 words of bases per warp tile
-constexpr int BLOOM_WORDS = 52736;         // 206 KB seed filter resident in shared memory
-constexpr int HL_CAP = 64;                 // per-warp ring of filter-hit ids (lane << 6 | lookup)
-constexpr int CQ_CAP = 64;                 // per-warp ring of verified seeds (position, offsets)
+constexpr int BLOOM_WORDS = 51712;         // 202 KB seed filter resident in shared memory
+constexpr int HL_CAP = 128;                // per-warp list of filter-hit ids of one tile
+constexpr int CQ_CAP = 64;                 // per-warp ring of verified seeds
 constexpr size_t SCAN_SMEM_BYTES =
     (size_t)BLOOM_WORDS * 4 + (size_t)SCAN_WARPS * CQ_CAP * 8 + (size_t)SCAN_WARPS * HL_CAP * 2;
 
+constexpr int MAX_SEED_LEN = 15;             // 30 bits: leaves SEED_EMPTY outside the seed space
 constexpr uint32_t SEED_MULT = 0x9E3779B1u;  // odd multiplier of the filter hash
 constexpr uint32_t SEED_MULT2 = 0x85EBCA77u; // second filter bit: bits 32..36 of hash * SEED_MULT2
-constexpr uint32_t SEEDTAB_MULT = 0xC2B2AE3Du; // seed table slot = (seed * SEEDTAB_MULT) >> shift
+constexpr uint32_t SEEDTAB_MULT = 0xC2B2AE3Du; // seed bucket = (seed * SEEDTAB_MULT) >> shift
+constexpr uint32_t SEED_EMPTY = 0xFFFFFFFFu;
 constexpr uint64_t KEY_EMPTY = ~0ull;        // keys use at most 62 bits
 constexpr uint32_t ENTRY_DEAD = 0xFFFFFFFFu; // repeated (key, owner) triple
+constexpr int BUCKET = 4;                    // slots per bucket in both tables
 
 // ---- hashes ----------------------------------------------------------------
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
@@ -43,8 +46,8 @@ __host__ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
   return x;
 }
 
-// slot of a seed in the exact seed table (multiplicative hash, top bits)
-__host__ __device__ __forceinline__ uint32_t seed_slot(uint32_t seed, uint32_t shift) {
+// bucket of a seed in the exact seed table (multiplicative hash, top bits)
+__host__ __device__ __forceinline__ uint32_t seed_bucket(uint32_t seed, uint32_t shift) {
   return (seed * SEEDTAB_MULT) >> shift;
 }
 
@@ -67,24 +70,41 @@ __device__ __forceinline__ uint64_t base_reverse(uint64_t v, int k) {
   return r >> (64 - 2 * k);
 }
 
+// ---- the two lookup structures (both in L2) -----------------------------------
+// Seed table: buckets of 4 uint32 seeds (16 B, one LDG.128); sinfo[slot] = bitmap
+// of the offsets j at which some key designates this seed.  A seed lives in
+// its home bucket or, when that is full, in the next one (linear in buckets).
+struct SeedTable {
+  uint32_t *seeds;
+  uint32_t *sinfo;
+  uint32_t bucket_mask;  // n_buckets - 1
+  uint32_t shift;        // 32 - log2(n_buckets)
+};
+// Key table: buckets of 4 canonical keys (32 B, two LDG.128), a multimap: one
+// slot per (key, owner) entry.  entry / offs are read only on a key match.
+struct KeyTable {
+  uint64_t *keys;
+  uint32_t *entry;  // entry index per slot
+  uint64_t *offs;   // designated seed offsets: 5 bits per class, orientation 1 at bit 32
+  uint32_t bucket_mask;
+};
+__host__ __device__ __forceinline__ uint32_t key_bucket(uint64_t key, uint32_t bucket_mask) {
+  return (uint32_t)mix64(key) & bucket_mask;
+}
+
 // ---- parameters of one scan launch -------------------------------------------
 struct ScanParams {
   const uint32_t *bases;  // 2-bit stream, 16 positions per word
   const uint32_t *mask;   // 1-bit validity stream, 32 positions per word
   uint32_t n_pos, n_bwords, n_mwords, n_tiles;
-  const uint32_t *bloom;    // BLOOM_WORDS words, copied into shared memory per CTA
-  const uint64_t *seedtab;  // (offset bitmap << 32) | seed, 0 = empty
-  uint32_t seedtab_mask;
-  uint32_t seedtab_shift;  // 32 - log2(slots)
+  const uint32_t *bloom;  // BLOOM_WORDS words, copied into shared memory per CTA
+  SeedTable st;
+  KeyTable kt;
   uint32_t seed_mult;  // SEED_MULT << (32 - 2s): the product ignores bases beyond s
   uint32_t seed_mask;  // low 2s bits
   uint32_t four;       // = 4, opaque to the compiler: keeps the filter address on the FMA pipe
-  const uint64_t *tkeys;  // canonical key per slot, KEY_EMPTY = empty
-  const uint32_t *tentry; // entry index per slot
-  const uint64_t *toffs;  // designated seed offsets: 5 bits per class, orientation 1 at bit 32
-  uint32_t table_mask;
-  uint32_t *counts;  // this sample's [n_entries] counters
-  int k;
+  uint32_t *counts;    // this sample's [n_entries] counters
+  int k, s;
   unsigned long long *prof;  // 4 counters or nullptr
 };
 

@@ -4,13 +4,14 @@
 //
 // Every stream position p with p % D == 0 has its s-mer tested against a
 // seed filter held in shared memory (stage A, the only per-position work).
-// Filter hits are compacted per warp and verified, 32 at a time, against the
-// exact seed table in L2 (stage B); a verified seed carries the offsets j at
-// which some table key designates it, and each window w = p - j is then
-// rebuilt from the stream, validated against the mask, canonicalised and
-// probed in the key table (stage C).  A slot is counted only when its own
-// designated offset for class (j % D) equals j, so a matching window is
-// counted exactly once however many seeds it contains (proof in DESIGN.md §4).
+// Filter hits are compacted per warp tile and verified, 32 at a time, against
+// the exact seed table in L2 (stage B, one 16-byte bucket load per hit, issued
+// one tile ahead of its use).  A verified seed carries the offsets j at which
+// some table key designates it; each window w = p - j is rebuilt from the
+// stream, validated against the mask, canonicalised and probed in the key
+// table (stage C).  A slot is counted only when its own designated offset for
+// class (j % D) equals j, so a matching window is counted exactly once however
+// many seeds it contains (proof in DESIGN.md §4).
 #pragma once
 #include "dkb_device.cuh"
 
@@ -20,11 +21,14 @@ template <int D, int NH, bool PROF>
 struct ScanWarp {
   const ScanParams &P;
   const uint32_t *filt;
-  uint16_t *hl;  // ring of filter-hit ids of the current tile: lane << 6 | lookup index
-  uint64_t *cq;  // ring of verified seeds: offset bitmap << 32 | position
-  uint32_t hh = 0, ht = 0, ch = 0, ct = 0;
+  uint16_t *hl;  // filter-hit ids of the current tile: lane << 6 | lookup index
+  uint64_t *cq;  // ring of verified seeds: seed-table slot << 32 | position
+  uint32_t ch = 0, ct = 0;
   int lane;
   uint32_t lt_mask;
+  // stage B probes in flight (issued at the end of one tile, consumed in the next)
+  uint32_t pend_n = 0, pend_x = 0, pend_p = 0, pend_b = 0;
+  uint4 pend_bucket = {0, 0, 0, 0};
   unsigned long long n_bloom = 0, n_seed = 0, n_probe = 0, n_hit = 0;
 
   __device__ __forceinline__ ScanWarp(const ScanParams &p, const uint32_t *f, uint16_t *h,
@@ -38,13 +42,24 @@ struct ScanWarp {
     return wi < P.n_mwords ? __ldg(P.mask + wi) : 0u;
   }
 
-  // ---- stage C: windows of up to n verified seeds ---------------------------
+  // ---- stage C: every candidate window of up to n verified seeds ----------------
+  // One lane per verified seed.  All windows of a seed at p lie in
+  // [p - (k - s), p + k): their bases and mask bits are fetched once (5 + 3
+  // words, issued together with the offset bitmap), then each window costs one
+  // key-bucket load.
   __device__ __forceinline__ void stage_c(uint32_t n) {
     if ((uint32_t)lane < n) {
       const uint64_t e = cq[(ch + lane) & (CQ_CAP - 1)];
       const uint32_t p = (uint32_t)e;
-      uint32_t info = (uint32_t)(e >> 32);
-      const int k = P.k;
+      const int k = P.k, E = k - P.s;
+      const uint32_t start = p > (uint32_t)E ? p - (uint32_t)E : 0u;
+      const uint32_t bw0 = start >> 4, mw0 = start >> 5;
+      uint32_t info = __ldg(P.st.sinfo + (uint32_t)(e >> 32));
+      uint32_t b[5], m[3];
+#pragma unroll
+      for (int i = 0; i < 5; i++) b[i] = ld_bases(bw0 + i);
+#pragma unroll
+      for (int i = 0; i < 3; i++) m[i] = ld_mask(mw0 + i);
       const uint64_t km = kmer_mask(k);
       const uint32_t vm = (1u << k) - 1;  // k <= 31
       while (info) {
@@ -55,32 +70,43 @@ struct ScanWarp {
         if (w + (uint32_t)k > P.n_pos) continue;
         if (PROF) n_probe++;
         // validity: mask bits w .. w+k-1 must all be set
-        const uint32_t mi = w >> 5, ms = w & 31;
-        const uint64_t m64 = ((uint64_t)ld_mask(mi + 1) << 32 | ld_mask(mi)) >> ms;
-        if (((uint32_t)m64 & vm) != vm) continue;
+        const uint32_t mo = w - (mw0 << 5);  // < 64
+        const uint32_t mbits = mo < 32 ? __funnelshift_r(m[0], m[1], mo)
+                                       : __funnelshift_r(m[1], m[2], mo - 32);
+        if ((mbits & vm) != vm) continue;
         // the window's bases in stream order (first base least significant)
-        const uint32_t wi = w >> 4, sh = 2 * (w & 15);
-        const uint64_t lo = (uint64_t)ld_bases(wi + 1) << 32 | ld_bases(wi);
-        uint64_t v = lo >> sh;
-        if (sh) v |= (uint64_t)ld_bases(wi + 2) << (64 - sh);
-        v &= km;
+        const uint32_t bo = w - (bw0 << 4);  // < 48
+        uint32_t x0 = b[0], x1 = b[1], x2 = b[2];
+        if (bo >= 16) { x0 = b[1]; x1 = b[2]; x2 = b[3]; }
+        if (bo >= 32) { x0 = b[2]; x1 = b[3]; x2 = b[4]; }
+        const uint32_t sh = 2 * (bo & 15);
+        const uint64_t v =
+            ((uint64_t)__funnelshift_r(x1, x2, sh) << 32 | __funnelshift_r(x0, x1, sh)) & km;
         const uint64_t fwd = base_reverse(v, k);
         const uint64_t rc = ~v & km;  // complement of the stream-order value IS the rc key
         const uint64_t key = fwd <= rc ? fwd : rc;
         const int sel = (fwd <= rc ? 0 : 32) + 5 * (j % D);
-        uint32_t slot = (uint32_t)mix64(key) & P.table_mask;
+        uint32_t bk = key_bucket(key, P.kt.bucket_mask);
         while (true) {
-          const uint64_t tk = __ldg(P.tkeys + slot);
-          if (tk == KEY_EMPTY) break;
-          if (tk == key) {
-            const uint32_t want = (uint32_t)(__ldg(P.toffs + slot) >> sel) & 31u;
-            const uint32_t ent = __ldg(P.tentry + slot);
-            if (want == (uint32_t)j && ent != ENTRY_DEAD) {
-              atomicAdd(P.counts + ent, 1u);
-              if (PROF) n_hit++;
+          const ulonglong2 *bp = reinterpret_cast<const ulonglong2 *>(P.kt.keys + bk * BUCKET);
+          const ulonglong2 k01 = __ldg(bp), k23 = __ldg(bp + 1);
+          const uint64_t ks[4] = {k01.x, k01.y, k23.x, k23.y};
+          bool open = false;
+#pragma unroll
+          for (int q = 0; q < BUCKET; q++) {
+            if (ks[q] == KEY_EMPTY) open = true;
+            if (ks[q] == key) {
+              const uint32_t slot = bk * BUCKET + q;
+              const uint32_t want = (uint32_t)(__ldg(P.kt.offs + slot) >> sel) & 31u;
+              const uint32_t ent = __ldg(P.kt.entry + slot);
+              if (want == (uint32_t)j && ent != ENTRY_DEAD) {
+                atomicAdd(P.counts + ent, 1u);
+                if (PROF) n_hit++;
+              }
             }
           }
-          slot = (slot + 1) & P.table_mask;
+          if (open) break;
+          bk = (bk + 1) & P.kt.bucket_mask;
         }
       }
     }
@@ -88,13 +114,48 @@ struct ScanWarp {
     __syncwarp();
   }
 
-  // ---- stage B: exact check of up to n filter hits of the current tile ------------
+  // ---- stage B, second half: use the seed buckets loaded one tile ago -----------
+  __device__ __forceinline__ void consume_pending() {
+    if (pend_n == 0) return;
+    bool found = false;
+    uint32_t slot = 0;
+    if ((uint32_t)lane < pend_n) {
+      uint4 bk = pend_bucket;
+      uint32_t b = pend_b;
+      while (true) {
+        const uint32_t base = b * BUCKET;
+        if (bk.x == pend_x) { found = true; slot = base; }
+        if (bk.y == pend_x) { found = true; slot = base + 1; }
+        if (bk.z == pend_x) { found = true; slot = base + 2; }
+        if (bk.w == pend_x) { found = true; slot = base + 3; }
+        // the home bucket has room, or the seed is here: done.  Full bucket
+        // without the seed (rare): it may have spilled into the next bucket.
+        if (found || bk.x == SEED_EMPTY || bk.y == SEED_EMPTY || bk.z == SEED_EMPTY ||
+            bk.w == SEED_EMPTY)
+          break;
+        b = (b + 1) & P.st.bucket_mask;
+        bk = __ldg(reinterpret_cast<const uint4 *>(P.st.seeds) + b);
+      }
+    }
+    pend_n = 0;
+    const uint32_t bal = __ballot_sync(FULL_MASK, found);
+    if (bal) {
+      if (found) cq[(ct + __popc(bal & lt_mask)) & (CQ_CAP - 1)] = (uint64_t)slot << 32 | pend_p;
+      ct += __popc(bal);
+      if (PROF && found) n_seed++;
+      __syncwarp();
+      if (ct - ch >= 32) stage_c(32);
+    }
+  }
+
+  // ---- stage B, first half: start the exact check of hits [first, first + n) ------
   // Each lane takes one hit id, pulls the 16 bases at that position out of the
-  // owning lane's registers with shuffles (no trip back to L2) and probes the
-  // seed table.  tile_base = stream position of lane 0's chunk.
-  __device__ __forceinline__ void stage_b(uint32_t n, const uint32_t (&w)[5], uint32_t tile_base) {
+  // owning lane's registers with shuffles (no trip back to L2) and issues the
+  // load of the seed's bucket.  tile_base = stream position of lane 0's chunk.
+  __device__ __forceinline__ void issue_probes(uint32_t first, uint32_t n, const uint32_t (&w)[5],
+                                               uint32_t tile_base) {
     const bool act = (uint32_t)lane < n;
-    const uint32_t id = act ? hl[(hh + lane) & (HL_CAP - 1)] : (uint32_t)lane << 6;
+    const uint32_t id = act ? hl[first + lane] : (uint32_t)lane << 6;
     const int src = id >> 6;
     const uint32_t q = (id & 63) * D;  // offset inside the owning lane's chunk
     const uint32_t c = q >> 4;
@@ -105,60 +166,61 @@ struct ScanWarp {
     if (c == 1) { lo = v[1]; hi = v[2]; }
     if (c == 2) { lo = v[2]; hi = v[3]; }
     if (c == 3) { lo = v[3]; hi = v[4]; }
-    const uint32_t x = __funnelshift_r(lo, hi, 2 * (q & 15)) & P.seed_mask;
-    const uint32_t p = tile_base + src * CHUNK + q;
-    bool found = false;
-    uint32_t info = 0;
-    if (act) {
-      uint32_t slot = seed_slot(x, P.seedtab_shift);
-      while (true) {
-        const uint64_t e = __ldg(P.seedtab + slot);
-        if (e == 0) break;
-        if ((uint32_t)e == x) {
-          found = true;
-          info = (uint32_t)(e >> 32);
-          break;
+    pend_x = __funnelshift_r(lo, hi, 2 * (q & 15)) & P.seed_mask;
+    pend_p = tile_base + src * CHUNK + q;
+    pend_b = seed_bucket(pend_x, P.st.shift);
+    if (act) pend_bucket = __ldg(reinterpret_cast<const uint4 *>(P.st.seeds) + pend_b);
+    pend_n = n;
+  }
+
+  // ---- compact this tile's filter hits and start their verification ---------------
+  // bit 31 of acc0 is lookup 0; acc1 (D == 1 only) continues at lookup 32.
+  __device__ __forceinline__ void handle_hits(uint32_t acc0, uint32_t acc1,
+                                              const uint32_t (&w)[5], uint32_t tile_base) {
+    const uint32_t cnt = __popc(acc0) + (D == 1 ? __popc(acc1) : 0);
+    if (PROF) n_bloom += cnt;
+    // inclusive prefix sum of the per-lane hit counts
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(FULL_MASK, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const uint32_t total = __shfl_sync(FULL_MASK, incl, 31);
+    if (total == 0) return;
+    const uint32_t excl = incl - cnt;
+    const uint32_t tag = (uint32_t)lane << 6;
+    // the id list holds HL_CAP hits; denser tiles (low-complexity sequence) take more passes
+    for (uint32_t base = 0; base < total; base += HL_CAP) {
+      uint32_t idx = excl - base;  // wraps below zero for hits of earlier passes
+      uint32_t a = acc0;
+      while (a) {
+        const int i = __clz(a);
+        a ^= 0x80000000u >> i;
+        if (idx < (uint32_t)HL_CAP) hl[idx] = (uint16_t)(tag + i);
+        idx++;
+      }
+      if (D == 1) {
+        a = acc1;
+        while (a) {
+          const int i = __clz(a);
+          a ^= 0x80000000u >> i;
+          if (idx < (uint32_t)HL_CAP) hl[idx] = (uint16_t)(tag + 32 + i);
+          idx++;
         }
-        slot = (slot + 1) & P.seedtab_mask;
       }
-    }
-    hh += n;
-    const uint32_t b = __ballot_sync(FULL_MASK, found);
-    if (b) {
-      if (found) cq[(ct + __popc(b & lt_mask)) & (CQ_CAP - 1)] = (uint64_t)info << 32 | p;
-      ct += __popc(b);
-      if (PROF && found) n_seed++;
       __syncwarp();
-      if (ct - ch >= 32) stage_c(32);
-    }
-  }
-
-  // ---- compact the set bits of one 32-lookup hit mask into the id ring -----------
-  // bit 31 of acc is lookup idx0, bit 30 lookup idx0 + 1, ...
-  __device__ __forceinline__ void push_hits(uint32_t acc, uint32_t idx0, const uint32_t (&w)[5],
-                                            uint32_t tile_base) {
-    if (PROF) n_bloom += __popc(acc);
-    const uint32_t tag = (uint32_t)lane << 6 | idx0;
-    while (true) {
-      const bool has = acc != 0;
-      const uint32_t b = __ballot_sync(FULL_MASK, has);
-      if (b == 0) break;
-      if (has) {
-        const int i = __clz(acc);
-        acc ^= 0x80000000u >> i;
-        hl[(ht + __popc(b & lt_mask)) & (HL_CAP - 1)] = (uint16_t)(tag + i);
+      const uint32_t here = min(total - base, (uint32_t)HL_CAP);
+      for (uint32_t r = 0; r < here; r += 32) {
+        consume_pending();  // at most one batch of probes in flight
+        issue_probes(r, min(here - r, 32u), w, tile_base);
       }
-      ht += __popc(b);
       __syncwarp();
-      if (ht - hh >= 32) stage_b(32, w, tile_base);
     }
-  }
-
-  __device__ __forceinline__ void flush_tile(const uint32_t (&w)[5], uint32_t tile_base) {
-    if (ht != hh) stage_b(ht - hh, w, tile_base);  // fewer than 32 left
   }
 
   __device__ __forceinline__ void drain() {
+    consume_pending();
     while (ct != ch) stage_c(min(ct - ch, 32u));
   }
 
@@ -243,10 +305,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
     halo_finish(lane, w);
     uint32_t acc0, acc1;
     W.stage_a(w, acc0, acc1);
-    const uint32_t tile_base = tile * WTILE;
-    W.push_hits(acc0, 0, w, tile_base);
-    if (D == 1) W.push_hits(acc1, 32, w, tile_base);
-    W.flush_tile(w, tile_base);
+    W.consume_pending();  // the previous tile's seed buckets have had a whole stage A to arrive
+    W.handle_hits(acc0, acc1, w, tile * WTILE);
   }
   W.drain();
 

@@ -9,7 +9,7 @@ from denovo_kmer_b200 import synth
 n_var = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 n_pos = int(float(sys.argv[2])) if len(sys.argv) > 2 else 1 << 30
 k = int(sys.argv[3]) if len(sys.argv) > 3 else 31
-tunings = [tuple(int(x) for x in t.split(',')) for t in sys.argv[4:]] or [(16,1,1),(16,1,2),(15,2,1),(15,2,2),(14,4,1),(14,4,2)]
+tunings = [tuple(int(x) for x in t.split(',')) for t in sys.argv[4:]] or [(15,1,1),(15,1,2),(15,2,1),(15,2,2),(14,4,1),(14,4,2)]
 dev = torch.device('cuda:0')
 genome = synth.make_genome(max(4_000_000, n_var * 400), 1)
 variants = synth.plant_variants(genome, n_var, k, 2)

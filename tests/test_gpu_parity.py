@@ -20,7 +20,7 @@ def _check(dkb, orc, trio, k, min_bq=20, drop_shared=True, **kw):
     return entries, ks, want, got, stats
 
 
-@pytest.mark.parametrize("tuning", [None, (16, 1, 1), (16, 1, 2), (15, 2, 1), (15, 2, 2),
+@pytest.mark.parametrize("tuning", [None, (15, 1, 1), (15, 1, 2), (13, 1, 2), (15, 2, 1), (15, 2, 2),
                                     (14, 4, 1), (14, 4, 2), (12, 1, 1), (9, 2, 1)])
 @pytest.mark.parametrize("hints", [True, False])
 def test_snv_trio_k31(dkb, orc, tuning, hints):
