@@ -2,6 +2,7 @@
 // No CPU fallback: every compute entry point needs a CUDA device.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -116,8 +117,29 @@ void free_table(dkb_ctx *c) {
   c->finalised = false;
 }
 
-// Resolve (s, D, NH): the caller's choice, else DKB_TUNING="s,D,NH", else auto.
-int resolve_tuning(dkb_ctx *ctx, size_t n_entries) {
+// Seed length for stride D: as long as the seed space allows (30 bits), but short
+// enough that a ladder of spacing floor((k-s+1)/D)*D covers an SNV's k windows
+// with two seeds per strand and class.
+int default_seed_len(int k, int D) {
+  int s = k - D + 1 < MAX_SEED_LEN ? k - D + 1 : MAX_SEED_LEN;
+  if (D == 4 && s > 14 && k - 14 + 1 >= 16) s = 14;
+  return s;
+}
+
+// Modelled warp-instructions per 2048-position warp tile (fitted to ncu counts,
+// profiles/README.md): filter lookups + handling of the filter's false positives.
+double tile_cost(double n_entries, bool hints, int k, int D, int NH) {
+  const double seeds = n_entries * (hints ? 2.6 : 6.2) * D / k;
+  const double bits = (double)BLOOM_WORDS * 32;
+  const double dens = 1.0 - exp(-NH * seeds / bits);
+  const double fp = pow(dens, NH) * 1.3 + 1e-4;  // 1.3: per-word load variance
+  const double lookups = 64.0 / D;
+  return lookups * (3.6 + 2.0 * NH) + 60.0 + 9.0 * (2048.0 / D) * fp;
+}
+
+// Resolve (s, D, NH): the caller's choice, else DKB_TUNING="s,D,NH", else the
+// cheapest combination under tile_cost().
+int resolve_tuning(dkb_ctx *ctx, size_t n_entries, bool hints) {
   dkb_tuning t = ctx->user_tuning;
   if (const char *e = getenv("DKB_TUNING")) {
     int a = 0, b = 0, c = 0;
@@ -128,25 +150,28 @@ int resolve_tuning(dkb_ctx *ctx, size_t n_entries) {
     }
   }
   const int k = ctx->k;
-  int D = t.stride;
-  if (D == 0) D = 1;
-  if (D != 1 && D != 2 && D != 4) return fail(ctx, DKB_EINVAL, "stride must be 1, 2 or 4");
-  int s = t.seed_len;
-  if (s == 0) {
-    s = k - D + 1 < MAX_SEED_LEN ? k - D + 1 : MAX_SEED_LEN;
-    // keep a ladder of exactly two seeds per strand and class possible for SNVs:
-    // spacing floor((k-s+1)/D)*D must reach 16 at k = 31
-    if (D == 4 && s > 14 && k - 14 + 1 >= 16) s = 14;
+  if (t.stride != 0 && t.stride != 1 && t.stride != 2 && t.stride != 4)
+    return fail(ctx, DKB_EINVAL, "stride must be 1, 2 or 4");
+  if (t.bloom_hashes < 0 || t.bloom_hashes > 4)
+    return fail(ctx, DKB_EINVAL, "bloom_hashes must be 1..4");
+  int best_D = 0, best_NH = 0;
+  double best = 1e300;
+  for (int D = 1; D <= 4; D *= 2) {
+    if (t.stride && t.stride != D) continue;
+    if (k - D + 1 < 8) continue;
+    for (int NH = 1; NH <= 2; NH++) {  // 3 and 4 never beat 2 in measurements; manual only
+      if (t.bloom_hashes && t.bloom_hashes != NH) continue;
+      const double c = tile_cost((double)n_entries, hints, k, D, NH);
+      if (c < best) { best = c; best_D = D; best_NH = NH; }
+    }
   }
+  int D = t.stride ? t.stride : best_D;
+  int NH = t.bloom_hashes ? t.bloom_hashes : best_NH;
+  if (D == 0) return fail(ctx, DKB_EINVAL, "no stride fits this k");
+  if (NH == 0) NH = 2;
+  int s = t.seed_len ? t.seed_len : default_seed_len(k, D);
   if (s < 8 || s > MAX_SEED_LEN || s > k - D + 1)
     return fail(ctx, DKB_EINVAL, "seed_len out of range (8..15 and <= k - stride + 1)");
-  int NH = t.bloom_hashes;
-  if (NH == 0) {
-    // two bits per seed pay once the filter holds more than ~1 seed per 50 bits
-    const double est_seeds = (double)n_entries * 0.25 * D;
-    NH = est_seeds > BLOOM_WORDS * 32 / 50.0 ? 2 : 1;
-  }
-  if (NH != 1 && NH != 2) return fail(ctx, DKB_EINVAL, "bloom_hashes must be 1 or 2");
   ctx->s = s;
   ctx->D = D;
   ctx->NH = NH;
@@ -195,7 +220,8 @@ typedef void (*scan_fn)(const ScanParams);
 scan_fn pick_scan(int D, int NH, bool prof) {
 #define PICK(d, h)                                                         \
   if (D == d && NH == h) return prof ? (scan_fn)k_scan<d, h, true> : (scan_fn)k_scan<d, h, false>;
-  PICK(1, 1) PICK(1, 2) PICK(2, 1) PICK(2, 2) PICK(4, 1) PICK(4, 2)
+  PICK(1, 1) PICK(1, 2) PICK(1, 3) PICK(1, 4) PICK(2, 1) PICK(2, 2) PICK(2, 3) PICK(2, 4)
+  PICK(4, 1) PICK(4, 2) PICK(4, 3) PICK(4, 4)
 #undef PICK
   return nullptr;
 }
@@ -367,7 +393,7 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
   CU(cudaStreamSynchronize(ctx->s_scan));
   CU(cudaStreamSynchronize(ctx->s_copy));
   free_table(ctx);
-  int rc = resolve_tuning(ctx, n);
+  int rc = resolve_tuning(ctx, n, win_index != nullptr);
   if (rc != DKB_OK) return rc;
 
   ctx->n_entries = n;

@@ -167,9 +167,7 @@ __global__ void k_assign_seeds(const BuildParams B, bool count_only, uint32_t *s
       offs |= (uint64_t)j << (5 * c);
       seedtab_insert(T, seed, 1u << j);
       const uint32_t h = seed * seed_mult;
-      uint32_t bits = bloom_bit1(seed);
-      if (n_hashes == 2) bits |= bloom_bit2(h);
-      atomicOr(bloom + __umulhi(h, (uint32_t)BLOOM_WORDS), bits);
+      atomicOr(bloom + __umulhi(h, (uint32_t)BLOOM_WORDS), bloom_bits(seed, h, n_hashes));
     }
   }
   if (!count_only)

@@ -18,11 +18,14 @@ constexpr int BLOOM_WORDS = 51712;         // 202 KB seed filter resident in sha
 constexpr int HL_CAP = 128;                // per-warp list of filter-hit ids of one tile
 constexpr int CQ_CAP = 64;                 // per-warp ring of verified seeds
 constexpr size_t SCAN_SMEM_BYTES =
-    (size_t)BLOOM_WORDS * 4 + (size_t)SCAN_WARPS * CQ_CAP * 8 + (size_t)SCAN_WARPS * HL_CAP * 2;
+    (size_t)BLOOM_WORDS * 4 + (size_t)SCAN_WARPS * CQ_CAP * 8 + (size_t)SCAN_WARPS * HL_CAP * 2 +
+    (size_t)SCAN_WARPS * 4;
 
 constexpr int MAX_SEED_LEN = 15;             // 30 bits: leaves SEED_EMPTY outside the seed space
 constexpr uint32_t SEED_MULT = 0x9E3779B1u;  // odd multiplier of the filter hash
-constexpr uint32_t SEED_MULT2 = 0x85EBCA77u; // second filter bit: bits 32..36 of hash * SEED_MULT2
+constexpr uint32_t SEED_MULT2 = 0x85EBCA77u; // filter bit n: bits 32..36 of hash * SEED_MULTn
+constexpr uint32_t SEED_MULT3 = 0xC2B2AE3Du;
+constexpr uint32_t SEED_MULT4 = 0x27D4EB2Fu;
 constexpr uint32_t SEEDTAB_MULT = 0xC2B2AE3Du; // seed bucket = (seed * SEEDTAB_MULT) >> shift
 constexpr uint32_t SEED_EMPTY = 0xFFFFFFFFu;
 constexpr uint64_t KEY_EMPTY = ~0ull;        // keys use at most 62 bits
@@ -55,8 +58,16 @@ __host__ __device__ __forceinline__ uint32_t seed_bucket(uint32_t seed, uint32_t
 __host__ __device__ __forceinline__ uint32_t bloom_bit1(uint32_t seed) {
   return 0x80000000u >> (seed & 31);
 }
-__host__ __device__ __forceinline__ uint32_t bloom_bit2(uint32_t h) {
-  return 0x80000000u >> ((uint32_t)(((uint64_t)h * SEED_MULT2) >> 32) & 31);
+__host__ __device__ __forceinline__ uint32_t bloom_bitn(uint32_t h, uint32_t mult) {
+  return 0x80000000u >> ((uint32_t)(((uint64_t)h * mult) >> 32) & 31);
+}
+// all filter bits of a seed (n_hashes in 1..4)
+__host__ __device__ __forceinline__ uint32_t bloom_bits(uint32_t seed, uint32_t h, int n_hashes) {
+  uint32_t bits = bloom_bit1(seed);
+  if (n_hashes >= 2) bits |= bloom_bitn(h, SEED_MULT2);
+  if (n_hashes >= 3) bits |= bloom_bitn(h, SEED_MULT3);
+  if (n_hashes >= 4) bits |= bloom_bitn(h, SEED_MULT4);
+  return bits;
 }
 
 __host__ __device__ __forceinline__ uint64_t kmer_mask(int k) { return (1ull << (2 * k)) - 1; }

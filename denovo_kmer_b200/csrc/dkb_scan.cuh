@@ -22,6 +22,7 @@ struct ScanWarp {
   const ScanParams &P;
   const uint32_t *filt;
   uint16_t *hl;  // filter-hit ids of the current tile: lane << 6 | lookup index
+  uint32_t *hl_count;  // shared-memory append cursor of hl (0 between tiles)
   uint64_t *cq;  // ring of verified seeds: seed-table slot << 32 | position
   uint32_t ch = 0, ct = 0;
   int lane;
@@ -32,8 +33,8 @@ struct ScanWarp {
   unsigned long long n_bloom = 0, n_seed = 0, n_probe = 0, n_hit = 0;
 
   __device__ __forceinline__ ScanWarp(const ScanParams &p, const uint32_t *f, uint16_t *h,
-                                      uint64_t *c, int l)
-      : P(p), filt(f), hl(h), cq(c), lane(l), lt_mask((1u << l) - 1) {}
+                                      uint32_t *hc, uint64_t *c, int l)
+      : P(p), filt(f), hl(h), hl_count(hc), cq(c), lane(l), lt_mask((1u << l) - 1) {}
 
   __device__ __forceinline__ uint32_t ld_bases(uint32_t wi) const {
     return wi < P.n_bwords ? __ldg(P.bases + wi) : 0u;
@@ -117,24 +118,35 @@ struct ScanWarp {
   // ---- stage B, second half: use the seed buckets loaded one tile ago -----------
   __device__ __forceinline__ void consume_pending() {
     if (pend_n == 0) return;
-    bool found = false;
-    uint32_t slot = 0;
-    if ((uint32_t)lane < pend_n) {
-      uint4 bk = pend_bucket;
-      uint32_t b = pend_b;
-      while (true) {
-        const uint32_t base = b * BUCKET;
-        if (bk.x == pend_x) { found = true; slot = base; }
-        if (bk.y == pend_x) { found = true; slot = base + 1; }
-        if (bk.z == pend_x) { found = true; slot = base + 2; }
-        if (bk.w == pend_x) { found = true; slot = base + 3; }
-        // the home bucket has room, or the seed is here: done.  Full bucket
-        // without the seed (rare): it may have spilled into the next bucket.
-        if (found || bk.x == SEED_EMPTY || bk.y == SEED_EMPTY || bk.z == SEED_EMPTY ||
-            bk.w == SEED_EMPTY)
-          break;
-        b = (b + 1) & P.st.bucket_mask;
-        bk = __ldg(reinterpret_cast<const uint4 *>(P.st.seeds) + b);
+    const bool act = (uint32_t)lane < pend_n;
+    const uint4 bk = pend_bucket;
+    const uint32_t x = pend_x;
+    int q = -1;
+    if (bk.w == x) q = 3;
+    if (bk.z == x) q = 2;
+    if (bk.y == x) q = 1;
+    if (bk.x == x) q = 0;
+    bool found = act && q >= 0;
+    uint32_t slot = pend_b * BUCKET + q;
+    // Full home bucket without the seed (about 1 probe in 600): it may have
+    // spilled into the following buckets.
+    const bool full = bk.x != SEED_EMPTY && bk.y != SEED_EMPTY && bk.z != SEED_EMPTY &&
+                      bk.w != SEED_EMPTY;
+    if (__any_sync(FULL_MASK, act && !found && full)) {
+      if (act && !found && full) {
+        uint32_t b = pend_b;
+        while (true) {
+          b = (b + 1) & P.st.bucket_mask;
+          const uint4 nb = __ldg(reinterpret_cast<const uint4 *>(P.st.seeds) + b);
+          const uint32_t v[4] = {nb.x, nb.y, nb.z, nb.w};
+          bool open = false;
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            if (v[i] == x) { found = true; slot = b * BUCKET + i; }
+            if (v[i] == SEED_EMPTY) open = true;
+          }
+          if (found || open) break;
+        }
       }
     }
     pend_n = 0;
@@ -244,7 +256,9 @@ struct ScanWarp {
         uint32_t word;
         asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(addr));
         uint32_t bit = word << (x & 31);
-        if (NH == 2) bit &= word << (__umulhi(h, SEED_MULT2) & 31);
+        if (NH >= 2) bit &= word << (__umulhi(h, SEED_MULT2) & 31);
+        if (NH >= 3) bit &= word << (__umulhi(h, SEED_MULT3) & 31);
+        if (NH >= 4) bit &= word << (__umulhi(h, SEED_MULT4) & 31);
         if ((c * 16 + t) / D < 32)
           acc0 = __funnelshift_l(bit, acc0, 1);
         else
@@ -285,13 +299,16 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
   uint32_t *filt = smem;
   uint64_t *cq_all = reinterpret_cast<uint64_t *>(smem + BLOOM_WORDS);
   uint16_t *hl_all = reinterpret_cast<uint16_t *>(cq_all + SCAN_WARPS * CQ_CAP);
+  uint32_t *hc_all = reinterpret_cast<uint32_t *>(hl_all + SCAN_WARPS * HL_CAP);
+  if (threadIdx.x < SCAN_WARPS) hc_all[threadIdx.x] = 0;
 
   for (int i = threadIdx.x; i < BLOOM_WORDS / 4; i += SCAN_THREADS)
     reinterpret_cast<uint4 *>(filt)[i] = __ldg(reinterpret_cast<const uint4 *>(P.bloom) + i);
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  ScanWarp<D, NH, PROF> W(P, filt, hl_all + warp * HL_CAP, cq_all + warp * CQ_CAP, lane);
+  ScanWarp<D, NH, PROF> W(P, filt, hl_all + warp * HL_CAP, hc_all + warp, cq_all + warp * CQ_CAP,
+                          lane);
 
   const uint32_t n_warps = gridDim.x * SCAN_WARPS;
   uint32_t tile = blockIdx.x * SCAN_WARPS + warp;
