@@ -134,7 +134,7 @@ double tile_cost(double n_entries, bool hints, int k, int D, int NH) {
   const double dens = 1.0 - exp(-NH * seeds / bits);
   const double fp = pow(dens, NH) * 1.3 + 1e-4;  // 1.3: per-word load variance
   const double lookups = 64.0 / D;
-  return lookups * (3.6 + 2.0 * NH) + 60.0 + 9.0 * (2048.0 / D) * fp;
+  return lookups * (3.6 + 2.0 * NH) + 100.0 + 7.5 * (2048.0 / D) * fp;
 }
 
 // Resolve (s, D, NH): the caller's choice, else DKB_TUNING="s,D,NH", else the

@@ -81,6 +81,37 @@ __device__ __forceinline__ uint64_t base_reverse(uint64_t v, int k) {
   return r >> (64 - 2 * k);
 }
 
+// ---- L2 residency hints ------------------------------------------------------------
+// The stream is read once (evict-first); the seed / key tables and the counters
+// are re-read for the whole launch and should stay in the 126 MB L2 (evict-last).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint4 ldg_v4_hint(const void *ptr, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(ptr), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldg_u32_hint(const void *ptr, uint64_t pol) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint64_t ldg_u64_hint(const void *ptr, uint64_t pol) {
+  uint64_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(ptr), "l"(pol));
+  return v;
+}
+
 // ---- the two lookup structures (both in L2) -----------------------------------
 // Seed table: buckets of 4 uint32 seeds (16 B, one LDG.128); sinfo[slot] = bitmap
 // of the offsets j at which some key designates this seed.  A seed lives in

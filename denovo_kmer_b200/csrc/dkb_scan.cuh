@@ -27,6 +27,7 @@ struct ScanWarp {
   uint32_t ch = 0, ct = 0;
   int lane;
   uint32_t lt_mask;
+  uint64_t keep = l2_policy_evict_last();  // cache policy of every table load
   // stage B probes in flight (issued at the end of one tile, consumed in the next)
   uint32_t pend_n = 0, pend_x = 0, pend_p = 0, pend_b = 0;
   uint4 pend_bucket = {0, 0, 0, 0};
@@ -55,7 +56,7 @@ struct ScanWarp {
       const int k = P.k, E = k - P.s;
       const uint32_t start = p > (uint32_t)E ? p - (uint32_t)E : 0u;
       const uint32_t bw0 = start >> 4, mw0 = start >> 5;
-      uint32_t info = __ldg(P.st.sinfo + (uint32_t)(e >> 32));
+      uint32_t info = ldg_u32_hint(P.st.sinfo + (uint32_t)(e >> 32), keep);
       uint32_t b[5], m[3];
 #pragma unroll
       for (int i = 0; i < 5; i++) b[i] = ld_bases(bw0 + i);
@@ -89,17 +90,18 @@ struct ScanWarp {
         const int sel = (fwd <= rc ? 0 : 32) + 5 * (j % D);
         uint32_t bk = key_bucket(key, P.kt.bucket_mask);
         while (true) {
-          const ulonglong2 *bp = reinterpret_cast<const ulonglong2 *>(P.kt.keys + bk * BUCKET);
-          const ulonglong2 k01 = __ldg(bp), k23 = __ldg(bp + 1);
-          const uint64_t ks[4] = {k01.x, k01.y, k23.x, k23.y};
+          const uint4 *bp = reinterpret_cast<const uint4 *>(P.kt.keys + bk * BUCKET);
+          const uint4 k01 = ldg_v4_hint(bp, keep), k23 = ldg_v4_hint(bp + 1, keep);
+          const uint64_t ks[4] = {(uint64_t)k01.y << 32 | k01.x, (uint64_t)k01.w << 32 | k01.z,
+                                  (uint64_t)k23.y << 32 | k23.x, (uint64_t)k23.w << 32 | k23.z};
           bool open = false;
 #pragma unroll
           for (int q = 0; q < BUCKET; q++) {
             if (ks[q] == KEY_EMPTY) open = true;
             if (ks[q] == key) {
               const uint32_t slot = bk * BUCKET + q;
-              const uint32_t want = (uint32_t)(__ldg(P.kt.offs + slot) >> sel) & 31u;
-              const uint32_t ent = __ldg(P.kt.entry + slot);
+              const uint32_t want = (uint32_t)(ldg_u64_hint(P.kt.offs + slot, keep) >> sel) & 31u;
+              const uint32_t ent = ldg_u32_hint(P.kt.entry + slot, keep);
               if (want == (uint32_t)j && ent != ENTRY_DEAD) {
                 atomicAdd(P.counts + ent, 1u);
                 if (PROF) n_hit++;
@@ -137,7 +139,7 @@ struct ScanWarp {
         uint32_t b = pend_b;
         while (true) {
           b = (b + 1) & P.st.bucket_mask;
-          const uint4 nb = __ldg(reinterpret_cast<const uint4 *>(P.st.seeds) + b);
+          const uint4 nb = ldg_v4_hint(reinterpret_cast<const uint4 *>(P.st.seeds) + b, keep);
           const uint32_t v[4] = {nb.x, nb.y, nb.z, nb.w};
           bool open = false;
 #pragma unroll
@@ -181,7 +183,7 @@ struct ScanWarp {
     pend_x = __funnelshift_r(lo, hi, 2 * (q & 15)) & P.seed_mask;
     pend_p = tile_base + src * CHUNK + q;
     pend_b = seed_bucket(pend_x, P.st.shift);
-    if (act) pend_bucket = __ldg(reinterpret_cast<const uint4 *>(P.st.seeds) + pend_b);
+    if (act) pend_bucket = ldg_v4_hint(reinterpret_cast<const uint4 *>(P.st.seeds) + pend_b, keep);
     pend_n = n;
   }
 
