@@ -34,9 +34,7 @@ struct dkb_ctx {
   uint8_t *d_allele = nullptr;
   uint8_t *d_dead = nullptr;
   // key table
-  uint64_t *d_tkeys = nullptr;
-  uint32_t *d_tentry = nullptr;
-  uint64_t *d_toffs = nullptr;
+  uint4 *d_tslots = nullptr;
   uint32_t table_slots = 0;
   // seeds
   uint32_t *d_seeds = nullptr, *d_sinfo = nullptr;
@@ -108,7 +106,7 @@ void dfree(T *&p) {
 
 void free_table(dkb_ctx *c) {
   dfree(c->d_keys); dfree(c->d_variant); dfree(c->d_allele); dfree(c->d_dead);
-  dfree(c->d_tkeys); dfree(c->d_tentry); dfree(c->d_toffs);
+  dfree(c->d_tslots);
   dfree(c->d_seeds); dfree(c->d_sinfo); dfree(c->d_bloom);
   dfree(c->d_counts); dfree(c->d_hits); dfree(c->d_distinct); dfree(c->d_nkmers);
   dfree(c->d_calls);
@@ -208,10 +206,8 @@ SeedTable seed_table(const dkb_ctx *ctx) {
 
 KeyTable key_table(const dkb_ctx *ctx) {
   KeyTable T;
-  T.keys = ctx->d_tkeys;
-  T.entry = ctx->d_tentry;
-  T.offs = ctx->d_toffs;
-  T.bucket_mask = ctx->table_slots / BUCKET - 1;
+  T.slots = ctx->d_tslots;
+  T.bucket_mask = ctx->table_slots / KBUCKET - 1;
   return T;
 }
 
@@ -399,7 +395,7 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
   ctx->n_entries = n;
   ctx->n_variants = n_variants;
   const size_t n1 = n ? n : 1, nv1 = n_variants ? n_variants : 1;
-  ctx->table_slots = pow2_at_least(4 * (uint64_t)n + 2);  // <= 1 entry per 4-slot bucket on average
+  ctx->table_slots = pow2_at_least(8 * (uint64_t)n + 2);  // <= 0.25 entries per 2-slot bucket
   uint16_t *d_wi = nullptr, *d_wc = nullptr;
   uint32_t *d_slot_of = nullptr;
   uint32_t *d_set = nullptr;
@@ -412,9 +408,7 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
     CU(cudaMalloc(&ctx->d_allele, n1));
     CU(cudaMalloc(&ctx->d_dead, n1));
     CU(cudaMalloc(&d_slot_of, n1 * 4));
-    CU(cudaMalloc(&ctx->d_tkeys, (size_t)ctx->table_slots * 8));
-    CU(cudaMalloc(&ctx->d_tentry, (size_t)ctx->table_slots * 4));
-    CU(cudaMalloc(&ctx->d_toffs, (size_t)ctx->table_slots * 8));
+    CU(cudaMalloc(&ctx->d_tslots, (size_t)ctx->table_slots * 16));
     CU(cudaMalloc(&ctx->d_bloom, (size_t)BLOOM_WORDS * 4));
     CU(cudaMalloc(&ctx->d_counts, n1 * 3 * 4));
     CU(cudaMalloc(&ctx->d_hits, nv1 * 6 * 4));
@@ -422,9 +416,7 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
     CU(cudaMalloc(&ctx->d_nkmers, nv1 * 2 * 4));
     CU(cudaMalloc(&ctx->d_calls, nv1));
     CU(cudaMalloc(&d_nseeds, 4));
-    CU(cudaMemsetAsync(ctx->d_tkeys, 0xFF, (size_t)ctx->table_slots * 8, st));
-    CU(cudaMemsetAsync(ctx->d_tentry, 0xFF, (size_t)ctx->table_slots * 4, st));
-    CU(cudaMemsetAsync(ctx->d_toffs, 0, (size_t)ctx->table_slots * 8, st));
+    CU(cudaMemsetAsync(ctx->d_tslots, 0xFF, (size_t)ctx->table_slots * 16, st));
     CU(cudaMemsetAsync(ctx->d_bloom, 0, (size_t)BLOOM_WORDS * 4, st));
     CU(cudaMemsetAsync(ctx->d_counts, 0, n1 * 3 * 4, st));
     CU(cudaMemsetAsync(ctx->d_dead, 0, n1, st));
@@ -494,7 +486,7 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
 int dkb_batch_submit_device(dkb_ctx *ctx, const uint32_t *d_bases2, const uint32_t *d_mask1,
                             uint64_t n_positions, int sample) {
   if (!ctx) return fail(nullptr, DKB_EINVAL, "ctx is null");
-  if (!ctx->d_tkeys) return fail(ctx, DKB_ESTATE, "dkb_table_build must come first");
+  if (!ctx->d_tslots) return fail(ctx, DKB_ESTATE, "dkb_table_build must come first");
   if (sample < 0 || sample >= DKB_N_SAMPLES) return fail(ctx, DKB_EINVAL, "sample must be 0, 1 or 2");
   if (n_positions == 0) return DKB_OK;
   if (n_positions > 0xFFFFF000ull) return fail(ctx, DKB_EINVAL, "batch too long (max 2^32 - 4096 positions)");
@@ -508,7 +500,7 @@ int dkb_batch_submit_device(dkb_ctx *ctx, const uint32_t *d_bases2, const uint32
 int dkb_batch_submit(dkb_ctx *ctx, const uint32_t *bases2, const uint32_t *mask1,
                      uint64_t n_positions, int sample) {
   if (!ctx) return fail(nullptr, DKB_EINVAL, "ctx is null");
-  if (!ctx->d_tkeys) return fail(ctx, DKB_ESTATE, "dkb_table_build must come first");
+  if (!ctx->d_tslots) return fail(ctx, DKB_ESTATE, "dkb_table_build must come first");
   if (sample < 0 || sample >= DKB_N_SAMPLES) return fail(ctx, DKB_EINVAL, "sample must be 0, 1 or 2");
   if (n_positions == 0) return DKB_OK;
   if (n_positions > 0xFFFFF000ull) return fail(ctx, DKB_EINVAL, "batch too long (max 2^32 - 4096 positions)");

@@ -31,11 +31,12 @@ __global__ void k_insert_entries(const BuildParams B) {
   const uint64_t key = B.keys[i];
   uint32_t b = key_bucket(key, B.kt.bucket_mask);
   while (true) {
-    for (int j = 0; j < BUCKET; j++) {
-      const uint32_t slot = b * BUCKET + j;
-      if (atomicCAS(reinterpret_cast<unsigned long long *>(B.kt.keys + slot), KEY_EMPTY, key) ==
+    for (int j = 0; j < KBUCKET; j++) {
+      const uint32_t slot = b * KBUCKET + j;
+      if (atomicCAS(reinterpret_cast<unsigned long long *>(B.kt.slots + slot), KEY_EMPTY, key) ==
           KEY_EMPTY) {
-        B.kt.entry[slot] = i;
+        B.kt.slots[slot].z = i;
+        B.kt.slots[slot].w = 0;  // packed offsets, OR-ed in by k_assign_seeds
         B.slot_of[i] = slot;
         return;
       }
@@ -53,13 +54,13 @@ __global__ void k_mark_repeats(const BuildParams B) {
   uint8_t dead = 0;
   bool open = false;
   while (!open && !dead) {
-    for (int j = 0; j < BUCKET; j++) {
-      const uint32_t slot = b * BUCKET + j;
-      const uint64_t tk = B.kt.keys[slot];
+    for (int j = 0; j < KBUCKET; j++) {
+      const uint4 sl = B.kt.slots[b * KBUCKET + j];
+      const uint64_t tk = slot_key(sl);
       if (tk == KEY_EMPTY) {
         open = true;
       } else if (tk == key) {
-        const uint32_t e = B.kt.entry[slot];
+        const uint32_t e = sl.z;
         if (e < i && B.variant[e] == B.variant[i] && B.allele[e] == B.allele[i]) dead = 1;
       }
     }
@@ -71,7 +72,7 @@ __global__ void k_mark_repeats(const BuildParams B) {
 __global__ void k_apply_dead(const BuildParams B) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B.n) return;
-  if (B.dead[i]) B.kt.entry[B.slot_of[i]] = ENTRY_DEAD;
+  if (B.dead[i]) B.kt.slots[B.slot_of[i]].z = ENTRY_DEAD;
 }
 
 // Insert (seed, offset bit) into the bucketised seed table.
@@ -139,7 +140,8 @@ __global__ void k_assign_seeds(const BuildParams B, bool count_only, uint32_t *s
     u = wi & 0x7FFFu;
     if (ori != hap_ori) u = nwin - 1 - u;  // same window seen on the other strand
   }
-  uint64_t offs = 0;
+  uint32_t offs = 0;
+  const int W = 32 / (2 * D);  // bits per packed offset field
   for (int c = 0; c < D; c++) {
     int j;
     if (ladder) {
@@ -164,15 +166,13 @@ __global__ void k_assign_seeds(const BuildParams B, bool count_only, uint32_t *s
     if (count_only) {
       seedset_insert(set, set_mask, seed, n_seeds);
     } else {
-      offs |= (uint64_t)j << (5 * c);
+      offs |= (uint32_t)(j / D) << (W * (ori * D + c));
       seedtab_insert(T, seed, 1u << j);
       const uint32_t h = seed * seed_mult;
       atomicOr(bloom + __umulhi(h, (uint32_t)BLOOM_WORDS), bloom_bits(seed, h, n_hashes));
     }
   }
-  if (!count_only)
-    atomicOr(reinterpret_cast<unsigned long long *>(B.kt.offs + B.slot_of[i]),
-             (unsigned long long)offs << (32 * ori));
+  if (!count_only) atomicOr(&B.kt.slots[B.slot_of[i]].w, offs);
 }
 
 // ---- kernel 3: finalise -----------------------------------------------------

@@ -30,7 +30,8 @@ constexpr uint32_t SEEDTAB_MULT = 0xC2B2AE3Du; // seed bucket = (seed * SEEDTAB_
 constexpr uint32_t SEED_EMPTY = 0xFFFFFFFFu;
 constexpr uint64_t KEY_EMPTY = ~0ull;        // keys use at most 62 bits
 constexpr uint32_t ENTRY_DEAD = 0xFFFFFFFFu; // repeated (key, owner) triple
-constexpr int BUCKET = 4;                    // slots per bucket in both tables
+constexpr int BUCKET = 4;                    // seeds per seed-table bucket (16 B)
+constexpr int KBUCKET = 2;                   // slots per key-table bucket (32 B, one L2 sector)
 
 // ---- hashes ----------------------------------------------------------------
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
@@ -122,16 +123,25 @@ struct SeedTable {
   uint32_t bucket_mask;  // n_buckets - 1
   uint32_t shift;        // 32 - log2(n_buckets)
 };
-// Key table: buckets of 4 canonical keys (32 B, two LDG.128), a multimap: one
-// slot per (key, owner) entry.  entry / offs are read only on a key match.
+// Key table: 16-byte slots {key lo, key hi, entry index, packed designated
+// offsets}, buckets of 2 slots = one 32-byte L2 sector (two LDG.128), a
+// multimap: one slot per (key, owner) entry; a full bucket spills into the next.
+// Packed offsets: field f = orientation * D + class, 32 / (2 D) bits wide, holds
+// j / D of the designated seed offset j = (j / D) * D + class.
 struct KeyTable {
-  uint64_t *keys;
-  uint32_t *entry;  // entry index per slot
-  uint64_t *offs;   // designated seed offsets: 5 bits per class, orientation 1 at bit 32
-  uint32_t bucket_mask;
+  uint4 *slots;
+  uint32_t bucket_mask;  // n_buckets - 1
 };
 __host__ __device__ __forceinline__ uint32_t key_bucket(uint64_t key, uint32_t bucket_mask) {
   return (uint32_t)mix64(key) & bucket_mask;
+}
+__host__ __device__ __forceinline__ uint64_t slot_key(const uint4 &s) {
+  return (uint64_t)s.y << 32 | s.x;
+}
+// designated offset stored in a slot for (orientation, class)
+__host__ __device__ __forceinline__ uint32_t slot_offset(uint32_t packed, int ori, int cls, int D) {
+  const int W = 32 / (2 * D);
+  return ((packed >> (W * (ori * D + cls))) & ((1u << W) - 1)) * D + cls;
 }
 
 // ---- parameters of one scan launch -------------------------------------------

@@ -87,28 +87,21 @@ struct ScanWarp {
         const uint64_t fwd = base_reverse(v, k);
         const uint64_t rc = ~v & km;  // complement of the stream-order value IS the rc key
         const uint64_t key = fwd <= rc ? fwd : rc;
-        const int sel = (fwd <= rc ? 0 : 32) + 5 * (j % D);
+        const int ori = fwd <= rc ? 0 : 1;
         uint32_t bk = key_bucket(key, P.kt.bucket_mask);
         while (true) {
-          const uint4 *bp = reinterpret_cast<const uint4 *>(P.kt.keys + bk * BUCKET);
-          const uint4 k01 = ldg_v4_hint(bp, keep), k23 = ldg_v4_hint(bp + 1, keep);
-          const uint64_t ks[4] = {(uint64_t)k01.y << 32 | k01.x, (uint64_t)k01.w << 32 | k01.z,
-                                  (uint64_t)k23.y << 32 | k23.x, (uint64_t)k23.w << 32 | k23.z};
-          bool open = false;
-#pragma unroll
-          for (int q = 0; q < BUCKET; q++) {
-            if (ks[q] == KEY_EMPTY) open = true;
-            if (ks[q] == key) {
-              const uint32_t slot = bk * BUCKET + q;
-              const uint32_t want = (uint32_t)(ldg_u64_hint(P.kt.offs + slot, keep) >> sel) & 31u;
-              const uint32_t ent = ldg_u32_hint(P.kt.entry + slot, keep);
-              if (want == (uint32_t)j && ent != ENTRY_DEAD) {
-                atomicAdd(P.counts + ent, 1u);
-                if (PROF) n_hit++;
-              }
-            }
+          const uint4 *bp = P.kt.slots + bk * KBUCKET;
+          const uint4 s0 = ldg_v4_hint(bp, keep), s1 = ldg_v4_hint(bp + 1, keep);
+          const uint64_t k0 = slot_key(s0), k1 = slot_key(s1);
+          if (k0 == key && s0.z != ENTRY_DEAD && slot_offset(s0.w, ori, j % D, D) == (uint32_t)j) {
+            atomicAdd(P.counts + s0.z, 1u);
+            if (PROF) n_hit++;
           }
-          if (open) break;
+          if (k1 == key && s1.z != ENTRY_DEAD && slot_offset(s1.w, ori, j % D, D) == (uint32_t)j) {
+            atomicAdd(P.counts + s1.z, 1u);
+            if (PROF) n_hit++;
+          }
+          if (k0 == KEY_EMPTY || k1 == KEY_EMPTY) break;  // bucket not full: nothing spilled
           bk = (bk + 1) & P.kt.bucket_mask;
         }
       }
