@@ -159,7 +159,7 @@ def make_trio_host(genome_len: int, depth: float, n_variants: int, k: int, seed:
 # ---------------------------------------------------------------------------------------
 def make_sample_device(haps_codes, n_reads: int, read_len: int, seed: int, device,
                        err_rate: float = 0.002, n_rate: float = 0.0005, lowq_frac: float = 0.03,
-                       rc_frac: float = 0.5, chunk_reads: int = 1 << 20):
+                       rc_frac: float = 0.5, chunk_reads: int = 1 << 20, return_meta: bool = False):
     """haps_codes: list of uint8 CUDA tensors of base codes 0..3 (one per haplotype).
     Returns (bases2 int32 tensor, mask1 int32 tensor, n_positions, n_bases) in the layout
     of include/dkb.h.  Same read model as `sample_reads`; low-quality and N bases only
@@ -179,12 +179,14 @@ def make_sample_device(haps_codes, n_reads: int, read_len: int, seed: int, devic
     ar = torch.arange(read_len, device=device)
     sh2 = (2 * torch.arange(16, device=device, dtype=torch.int64))
     sh1 = torch.arange(32, device=device, dtype=torch.int64)
+    meta_h, meta_s = [], []
     for r0 in range(0, n_reads, chunk_reads):
         nr = min(chunk_reads, n_reads - r0)
         codes = torch.zeros((nr, stride), dtype=torch.uint8, device=device)
         valid = torch.zeros((nr, stride), dtype=torch.bool, device=device)
         hap_of = torch.randint(0, len(haps_codes), (nr,), generator=g, device=device)
         body = torch.empty((nr, read_len), dtype=torch.uint8, device=device)
+        all_starts = torch.zeros((nr,), dtype=torch.int64, device=device)
         for h, hap in enumerate(haps_codes):
             sel = (hap_of == h).nonzero().squeeze(1)
             if sel.numel() == 0:
@@ -192,6 +194,10 @@ def make_sample_device(haps_codes, n_reads: int, read_len: int, seed: int, devic
             starts = torch.randint(0, hap.numel() - read_len + 1, (sel.numel(),), generator=g,
                                    device=device)
             body[sel] = hap[starts[:, None] + ar[None, :]]
+            all_starts[sel] = starts
+        if return_meta:
+            meta_h.append(hap_of)
+            meta_s.append(all_starts)
         err = torch.rand((nr, read_len), generator=g, device=device) < err_rate
         bump = torch.randint(1, 4, (nr, read_len), generator=g, device=device, dtype=torch.uint8)
         body = torch.where(err, (body + bump) & 3, body)
@@ -215,4 +221,6 @@ def make_sample_device(haps_codes, n_reads: int, read_len: int, seed: int, devic
         assert p0 % 128 == 0
         bases2[p0 // 16: p0 // 16 + wb.numel()] = wb[: bases2.numel() - p0 // 16]
         mask1[p0 // 32: p0 // 32 + wm.numel()] = wm[: mask1.numel() - p0 // 32]
+    if return_meta:
+        return bases2, mask1, n_pos, n_reads * read_len, (torch.cat(meta_h), torch.cat(meta_s))
     return bases2, mask1, n_pos, n_reads * read_len

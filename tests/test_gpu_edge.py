@@ -1,0 +1,163 @@
+"""-m gpu: edge cases of the CUDA path against the oracle — empty and degenerate inputs,
+low-complexity sequence (dense filter hits: the multi-pass compaction path), keys shared
+by many owners, repeated triples, maximum-length batches of tiny reads."""
+import numpy as np
+import pytest
+
+import denovo_kmer_b200 as dkb_mod
+from denovo_kmer_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(dkb, orc, entries, reads, k, min_bq=20, tuning=None, hints=True):
+    """reads: list of 3 (seq, qual, offsets); returns (gpu counts, oracle counts)."""
+    ks = orc.KmerSet(entries.keys, entries.variant, entries.allele)
+    want = np.zeros((3, len(entries)), dtype=np.uint64)
+    with dkb.KmerCounter(k, tuning=tuning) as kc:
+        kc.build_table(entries, use_window_hints=hints)
+        for smp, (seq, qual, off) in enumerate(reads):
+            ks.count_reads(seq, qual, off, k, min_bq, counts=want[smp])
+            kc.submit(dkb.pack_reads(seq, qual, off, min_bq), smp)
+        got = kc.entry_counts()
+        res = kc.finalise(dkb.DEFAULT_THRESHOLDS)
+    return got, want, ks, res
+
+
+def _ascii(s):
+    return np.frombuffer(s.encode(), dtype=np.uint8)
+
+
+def test_empty_inputs(dkb, orc):
+    ent = dkb.variant_kmers([("ACGTACGTACGTACGTACGTACGTACGTAC", "A", "G", "TTGACCATGACCATTGACCATGACCAGGTT")], 31)
+    empty = (np.zeros(0, np.uint8), None, np.zeros(1, np.uint64))
+    got, want, _, _ = _run(dkb, orc, ent, [empty, empty, empty], 31)
+    assert got.sum() == 0 and want.sum() == 0
+    # empty table, non-empty reads
+    none = dkb.KmerEntries(np.zeros(0, np.uint64), np.zeros(0, np.uint32), np.zeros(0, np.uint8),
+                           None, None, 0)
+    seq = _ascii("ACGT" * 50)
+    r = (seq, None, np.array([0, len(seq)], dtype=np.uint64))
+    with dkb.KmerCounter(31) as kc:
+        kc.build_table(none)
+        kc.submit(dkb.pack_reads(*r, 20), 0)
+        assert kc.entry_counts().shape == (3, 0)
+        hits, dist, nk, calls = kc.finalise()
+        assert len(calls) == 0
+
+
+def test_reads_shorter_than_k_and_all_masked(dkb, orc):
+    trio = synth.make_trio_host(20_000, 10, 5, 31, seed=41)
+    ent = dkb.variant_kmers(trio.variant_tuples(), 31)
+    seq, qual, off = trio.reads[0]
+    # (a) every read cut to 30 bases: no 31-mer exists
+    n = len(off) - 1
+    short_off = np.arange(0, 30 * (n + 1), 30, dtype=np.uint64)
+    short_seq = seq.reshape(n, 150)[:, :30].reshape(-1).copy()
+    short_q = qual.reshape(n, 150)[:, :30].reshape(-1).copy()
+    # (b) all qualities below the threshold
+    low_q = np.full_like(qual, 5)
+    got, want, _, _ = _run(dkb, orc, ent, [(short_seq, short_q, short_off), (seq, low_q, off),
+                                            (seq, qual, off)], 31)
+    assert np.array_equal(got.astype(np.uint64), want)
+    assert got[0].sum() == 0 and got[1].sum() == 0 and got[2].sum() > 0
+
+
+@pytest.mark.parametrize("tuning", [None, (15, 1, 1), (15, 2, 2), (14, 4, 2), (8, 4, 1)])
+def test_low_complexity_dense_hits(dkb, orc, tuning):
+    """Poly-A / dinucleotide / short tandem repeats: the same seed recurs at every position,
+    filter hits exceed the per-tile id list, keys repeat inside one allele."""
+    k = 21
+    rng = np.random.default_rng(7)
+    unit = lambda u, n: (u * (n // len(u) + 1))[:n]
+    variants = [
+        (unit("A", 20), "A", "C", unit("A", 20)),            # poly-A flanks
+        (unit("AC", 20), "A", "G", unit("CA", 20)),           # dinucleotide repeat
+        (unit("ACG", 20), "ACG", "A", unit("ACG", 20)),       # tandem-repeat deletion
+        (unit("T", 20), "T", "TTT", unit("T", 20)),           # homopolymer insertion
+        ("".join("ACGT"[i] for i in rng.integers(0, 4, 20)), "G", "T",
+         "".join("ACGT"[i] for i in rng.integers(0, 4, 20))),
+    ]
+    for drop in (True, False):
+        ent = dkb.variant_kmers(variants, k, drop_shared=drop)
+        reads = []
+        for smp in range(3):
+            parts = [unit("A", 3000), unit("AC", 3000), unit("ACG", 3000), unit("T", 2000) + "C" + unit("A", 500),
+                     variants[4][0] + "T" + variants[4][3], unit("CA", 777), unit("GT", 1500)]
+            seqs = [p for p in parts for _ in range(3 + smp)]
+            off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+            off[1:] = np.cumsum([len(s) for s in seqs])
+            reads.append((_ascii("".join(seqs)), None, off))
+        got, want, _, _ = _run(dkb, orc, ent, reads, k, tuning=tuning, hints=True)
+        assert np.array_equal(got.astype(np.uint64), want), np.nonzero(got != want)
+        got, want, _, _ = _run(dkb, orc, ent, reads, k, tuning=tuning, hints=False)
+        assert np.array_equal(got.astype(np.uint64), want)
+        assert want.sum() > 1000
+
+
+def test_shared_keys_and_repeated_triples(dkb, orc):
+    """One key owned by several (variant, allele) pairs; exact triples repeated."""
+    k = 25
+    trio = synth.make_trio_host(30_000, 12, 8, k, seed=43)
+    ent = dkb.variant_kmers(trio.variant_tuples(), k)
+    # every entry duplicated under two more variant ids + an exact repeat of the first 40
+    nv = ent.n_variants
+    keys = np.concatenate([ent.keys, ent.keys, ent.keys, ent.keys[:40]])
+    var = np.concatenate([ent.variant, ent.variant + nv, (ent.variant + 1) % nv + 2 * nv,
+                          ent.variant[:40]])
+    al = np.concatenate([ent.allele, ent.allele, 1 - ent.allele, ent.allele[:40]])
+    multi = dkb.KmerEntries(keys, var, al, None, None, 3 * nv)
+    got, want, ks, res = _run(dkb, orc, multi, [trio.reads[s] for s in range(3)], k)
+    assert np.array_equal(got.astype(np.uint64), want)
+    n = len(ent)
+    assert np.array_equal(got[:, :n], got[:, n:2 * n]) and got[:, 3 * n:].sum() == 0
+    live = ks.live()
+    assert live[: 3 * n].all() and not live[3 * n:].any()
+    hits, dist, nk, calls = res
+    o_hits, o_dist, o_nk = ks.variant_stats(want, 3 * nv)
+    assert np.array_equal(hits.astype(np.uint64), o_hits) and np.array_equal(dist.astype(np.uint64), o_dist)
+    assert np.array_equal(nk, o_nk)
+    assert np.array_equal(calls, orc.calls(o_hits, o_dist, dkb.DEFAULT_THRESHOLDS))
+
+
+def test_many_tiny_reads_and_batch_boundaries(dkb, orc):
+    """Reads of length exactly k and k+1, submitted in batches of odd sizes: windows must
+    never span a read separator or a batch boundary."""
+    k = 15
+    trio = synth.make_trio_host(10_000, 5, 6, k, seed=45)
+    ent = dkb.variant_kmers(trio.variant_tuples(), k)
+    g = trio.genome
+    rng = np.random.default_rng(3)
+    starts = rng.integers(0, len(g) - 20, size=40_000)
+    lens = rng.integers(k, k + 2, size=len(starts))
+    off = np.zeros(len(starts) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(lens)
+    seq = np.concatenate([g[s:s + l] for s, l in zip(starts, lens)])
+    ks = orc.KmerSet(ent.keys, ent.variant, ent.allele)
+    want = ks.count_reads(seq, None, off, k, 0)
+    with dkb.KmerCounter(k) as kc:
+        kc.build_table(ent)
+        cuts = [0, 1, 2, 129, 130, 5000, 5001, 39_999, 40_000]
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            lo, hi = int(off[a]), int(off[b])
+            kc.submit(dkb.pack_reads(seq[lo:hi], None, off[a:b + 1] - off[a], 0), 0)
+        got = kc.entry_counts()[0]
+    assert np.array_equal(got.astype(np.uint64), want) and want.sum() > 0
+
+
+def test_state_errors(dkb):
+    from denovo_kmer_b200 import _lib
+    with dkb.KmerCounter(31) as kc:
+        st = dkb.pack_reads(_ascii("ACGT" * 20), None, np.array([0, 80], dtype=np.uint64), 0)
+        with pytest.raises(dkb.DkbError) as ei:
+            kc.submit(st, 0)
+        assert ei.value.code == _lib.ESTATE
+        ent = dkb.variant_kmers([("ACGTACGTACGTACGTACGTACGTACGTAC", "A", "G", "TTGACCATGACCATTGACCATGACCAGGTT")], 31)
+        kc.build_table(ent)
+        with pytest.raises(dkb.DkbError) as ei:
+            kc.submit(st, 3)
+        assert ei.value.code == _lib.EINVAL
+        with pytest.raises(dkb.DkbError):
+            kc.results()  # finalise has not run
+        with pytest.raises(dkb.DkbError):
+            kc.set_tuning(16, 1, 1) or kc.build_table(ent)  # seed_len 16 is outside 8..15
