@@ -1,0 +1,13 @@
+# Round profile: launch list of our kernels + full ncu capture of the scan kernel, both on
+# the bench command.  Usage (under gpurun): bash scripts/profile_round.sh r1
+R=${1:-r1}
+cd /root/repo
+mkdir -p gpurun_out
+CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
+$CMD > gpurun_out/plain_$R.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 200 --csv --log-file gpurun_out/launches_$R.csv $CMD > gpurun_out/ncu_launch_$R.log 2>&1
+echo "ncu launches rc=$?"
+$CMD > gpurun_out/plain2_$R.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:k_scan -s 9 -c 3 -o gpurun_out/prof_scan_$R $CMD > gpurun_out/ncu_full_$R.log 2>&1
+echo "ncu full rc=$?"
+tail -1 gpurun_out/plain_$R.log
