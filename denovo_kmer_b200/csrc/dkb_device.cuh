@@ -18,8 +18,7 @@ constexpr int BLOOM_WORDS = 51712;         // 202 KB seed filter resident in sha
 constexpr int HL_CAP = 128;                // per-warp list of filter-hit ids of one tile
 constexpr int CQ_CAP = 64;                 // per-warp ring of verified seeds
 constexpr size_t SCAN_SMEM_BYTES =
-    (size_t)BLOOM_WORDS * 4 + (size_t)SCAN_WARPS * CQ_CAP * 8 + (size_t)SCAN_WARPS * HL_CAP * 2 +
-    (size_t)SCAN_WARPS * 4;
+    (size_t)BLOOM_WORDS * 4 + (size_t)SCAN_WARPS * CQ_CAP * 8 + (size_t)SCAN_WARPS * HL_CAP * 2;
 
 constexpr int MAX_SEED_LEN = 15;             // 30 bits: leaves SEED_EMPTY outside the seed space
 constexpr uint32_t SEED_MULT = 0x9E3779B1u;  // odd multiplier of the filter hash
@@ -34,14 +33,6 @@ constexpr int BUCKET = 4;                    // seeds per seed-table bucket (16 
 constexpr int KBUCKET = 2;                   // slots per key-table bucket (32 B, one L2 sector)
 
 // ---- hashes ----------------------------------------------------------------
-__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
-  x ^= x >> 33;
-  x *= 0xff51afd7ed558ccdULL;
-  x ^= x >> 33;
-  x *= 0xc4ceb9fe1a85ec53ULL;
-  x ^= x >> 33;
-  return x;
-}
 __host__ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
   x *= 0x85EBCA6Bu;
   x ^= x >> 15;
@@ -132,8 +123,13 @@ struct KeyTable {
   uint4 *slots;
   uint32_t bucket_mask;  // n_buckets - 1
 };
+// Keys are genome k-mers (already well spread): a 32-bit fold-multiply is enough and
+// costs a fifth of a 64-bit finaliser in stage C.
 __host__ __device__ __forceinline__ uint32_t key_bucket(uint64_t key, uint32_t bucket_mask) {
-  return (uint32_t)mix64(key) & bucket_mask;
+  uint32_t x = (uint32_t)key ^ ((uint32_t)(key >> 32) * 0x9E3779B1u);
+  x *= 0x85EBCA6Bu;
+  x ^= x >> 15;
+  return x & bucket_mask;
 }
 __host__ __device__ __forceinline__ uint64_t slot_key(const uint4 &s) {
   return (uint64_t)s.y << 32 | s.x;

@@ -22,7 +22,6 @@ struct ScanWarp {
   const ScanParams &P;
   const uint32_t *filt;
   uint16_t *hl;  // filter-hit ids of the current tile: lane << 6 | lookup index
-  uint32_t *hl_count;  // shared-memory append cursor of hl (0 between tiles)
   uint64_t *cq;  // ring of verified seeds: seed-table slot << 32 | position
   uint32_t ch = 0, ct = 0;
   int lane;
@@ -34,8 +33,8 @@ struct ScanWarp {
   unsigned long long n_bloom = 0, n_seed = 0, n_probe = 0, n_hit = 0;
 
   __device__ __forceinline__ ScanWarp(const ScanParams &p, const uint32_t *f, uint16_t *h,
-                                      uint32_t *hc, uint64_t *c, int l)
-      : P(p), filt(f), hl(h), hl_count(hc), cq(c), lane(l), lt_mask((1u << l) - 1) {}
+                                      uint64_t *c, int l)
+      : P(p), filt(f), hl(h), cq(c), lane(l), lt_mask((1u << l) - 1) {}
 
   __device__ __forceinline__ uint32_t ld_bases(uint32_t wi) const {
     return wi < P.n_bwords ? __ldg(P.bases + wi) : 0u;
@@ -186,16 +185,25 @@ struct ScanWarp {
                                               const uint32_t (&w)[5], uint32_t tile_base) {
     const uint32_t cnt = __popc(acc0) + (D == 1 ? __popc(acc1) : 0);
     if (PROF) n_bloom += cnt;
-    // inclusive prefix sum of the per-lane hit counts
-    uint32_t incl = cnt;
+    // Exclusive prefix sum of the per-lane hit counts.  Counts are almost always
+    // below 8, so three ballots of their bit planes replace five dependent shuffles.
+    const uint32_t b0 = __ballot_sync(FULL_MASK, cnt & 1), b1 = __ballot_sync(FULL_MASK, cnt & 2),
+                   b2 = __ballot_sync(FULL_MASK, cnt & 4), bhi = __ballot_sync(FULL_MASK, cnt > 7);
+    if ((b0 | b1 | b2 | bhi) == 0) return;
+    uint32_t total, excl;
+    if (bhi == 0) {
+      total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+      excl = __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
+    } else {
+      uint32_t incl = cnt;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(FULL_MASK, incl, o);
-      if (lane >= o) incl += t;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL_MASK, incl, o);
+        if (lane >= o) incl += t;
+      }
+      total = __shfl_sync(FULL_MASK, incl, 31);
+      excl = incl - cnt;
     }
-    const uint32_t total = __shfl_sync(FULL_MASK, incl, 31);
-    if (total == 0) return;
-    const uint32_t excl = incl - cnt;
     const uint32_t tag = (uint32_t)lane << 6;
     // the id list holds HL_CAP hits; denser tiles (low-complexity sequence) take more passes
     for (uint32_t base = 0; base < total; base += HL_CAP) {
@@ -236,12 +244,12 @@ struct ScanWarp {
   // that start in the chunk and end beyond it).
   __device__ __forceinline__ void stage_a(const uint32_t (&w)[5], uint32_t &acc0,
                                           uint32_t &acc1) const {
-    acc0 = 0;
-    acc1 = 0;
     const uint32_t mult = P.seed_mult;
     const uint32_t fbase = (uint32_t)__cvta_generic_to_shared(filt);
+    uint32_t part[4];  // per-word hit bits (16 / D each): four short dependency chains
 #pragma unroll
     for (int c = 0; c < 4; c++) {
+      uint32_t a = 0;
 #pragma unroll
       for (int t = 0; t < 16; t += D) {
         const uint32_t x = t ? __funnelshift_r(w[c], w[c + 1], 2 * t) : w[c];
@@ -254,13 +262,19 @@ struct ScanWarp {
         if (NH >= 2) bit &= word << (__umulhi(h, SEED_MULT2) & 31);
         if (NH >= 3) bit &= word << (__umulhi(h, SEED_MULT3) & 31);
         if (NH >= 4) bit &= word << (__umulhi(h, SEED_MULT4) & 31);
-        if ((c * 16 + t) / D < 32)
-          acc0 = __funnelshift_l(bit, acc0, 1);
-        else
-          acc1 = __funnelshift_l(bit, acc1, 1);
+        a = __funnelshift_l(bit, a, 1);
       }
+      part[c] = a;
     }
-    if constexpr (64 / D < 32) acc0 <<= (32 - 64 / D);
+    // lookup 0 ends up in bit 31 of acc0
+    constexpr int NB = 16 / D;  // hit bits per word
+    if constexpr (D == 1) {
+      acc0 = part[0] << 16 | part[1];
+      acc1 = part[2] << 16 | part[3];
+    } else {
+      acc0 = (part[0] << (3 * NB) | part[1] << (2 * NB) | part[2] << NB | part[3]) << (32 - 4 * NB);
+      acc1 = 0;
+    }
   }
 };
 
@@ -294,16 +308,13 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
   uint32_t *filt = smem;
   uint64_t *cq_all = reinterpret_cast<uint64_t *>(smem + BLOOM_WORDS);
   uint16_t *hl_all = reinterpret_cast<uint16_t *>(cq_all + SCAN_WARPS * CQ_CAP);
-  uint32_t *hc_all = reinterpret_cast<uint32_t *>(hl_all + SCAN_WARPS * HL_CAP);
-  if (threadIdx.x < SCAN_WARPS) hc_all[threadIdx.x] = 0;
 
   for (int i = threadIdx.x; i < BLOOM_WORDS / 4; i += SCAN_THREADS)
     reinterpret_cast<uint4 *>(filt)[i] = __ldg(reinterpret_cast<const uint4 *>(P.bloom) + i);
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  ScanWarp<D, NH, PROF> W(P, filt, hl_all + warp * HL_CAP, hc_all + warp, cq_all + warp * CQ_CAP,
-                          lane);
+  ScanWarp<D, NH, PROF> W(P, filt, hl_all + warp * HL_CAP, cq_all + warp * CQ_CAP, lane);
 
   const uint32_t n_warps = gridDim.x * SCAN_WARPS;
   uint32_t tile = blockIdx.x * SCAN_WARPS + warp;
