@@ -198,6 +198,9 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL_DEBUG=VERSION/INFO prints to stdout; rank 0's stdout must be the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         tdist.init_process_group("nccl", device_id=dev)
 
     genome, variants, entries = build_table_inputs(a)

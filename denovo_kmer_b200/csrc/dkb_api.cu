@@ -115,24 +115,38 @@ void free_table(dkb_ctx *c) {
   c->finalised = false;
 }
 
-// Seed length for stride D: as long as the seed space allows (30 bits), but short
-// enough that a ladder of spacing floor((k-s+1)/D)*D covers an SNV's k windows
-// with two seeds per strand and class.
-int default_seed_len(int k, int D) {
-  int s = k - D + 1 < MAX_SEED_LEN ? k - D + 1 : MAX_SEED_LEN;
-  if (D == 4 && s > 14 && k - 14 + 1 >= 16) s = 14;
-  return s;
+// Ladder seeds one SNV-sized haplotype strand needs (k windows) at stride D, seed length s.
+double ladder_seeds_per_strand(int k, int s, int D) {
+  const int E = k - s, G = ((E + 1) / D) * D, nwin = k;
+  double n = 0;
+  for (int r = 0; r < D; r++) {
+    const int base = E - ((E - r) % D);  // first ladder element of residue r
+    n += 1 + (nwin - 1 > base ? (nwin - 1 - base + G - 1) / G : 0);
+  }
+  return n;
 }
 
-// Modelled warp-instructions per 2048-position warp tile (fitted to ncu counts,
-// profiles/README.md): filter lookups + handling of the filter's false positives.
-double tile_cost(double n_entries, bool hints, int k, int D, int NH) {
-  const double seeds = n_entries * (hints ? 2.6 : 6.2) * D / k;
+// Modelled cost of one 2048-position warp tile: filter lookups + handling of the filter's false positives +
+// stage C work for s-mers of unrelated sequence that equal a seed by chance.
+double tile_cost(double n_entries, bool hints, int k, int s, int D, int NH, double *seeds_out) {
+  const double n_haps = n_entries / k;  // allele haplotypes (SNV-sized)
+  // both strands; ref/alt haplotypes share the seeds that avoid the variant base (x0.7)
+  double seeds = n_haps * 2.0 * 0.7 * ladder_seeds_per_strand(k, s, D);
+  if (!hints) seeds *= 2.3;  // min-hash rule: ~2/(w+1) density instead of 1/w
+  if (seeds_out) *seeds_out = seeds;
   const double bits = (double)BLOOM_WORDS * 32;
   const double dens = 1.0 - exp(-NH * seeds / bits);
   const double fp = pow(dens, NH) * 1.3 + 1e-4;  // 1.3: per-word load variance
-  const double lookups = 64.0 / D;
-  return lookups * (3.6 + 2.0 * NH) + 100.0 + 7.5 * (2048.0 / D) * fp;
+  const double lookups_lane = 64.0 / D, lookups_tile = 2048.0 / D;
+  const double hits = lookups_tile * fp;
+  const double chance = seeds / pow(4.0, s);  // P(random s-mer is a seed)
+  // Cycles per warp tile and scheduler, fitted to measured scan times (profiles/README.md).
+  // A filter lookup is bound by shared-memory wavefronts (bank conflicts), not by its ~8
+  // instructions; the first 32 false positives of a tile ride the pipelined probe batch,
+  // later ones wait for L2; a seed table beyond ~16 MB stops being L2-friendly.
+  const double per_hit = 4.4 * (seeds > 5e5 ? 1.6 : 1.0);
+  return 136.0 + lookups_lane * (29.0 + 2.0 * NH) + per_hit * (hits < 32 ? hits : 32) +
+         (hits > 32 ? 9.0 * (hits - 32) : 0.0) + 25.0 * lookups_tile * chance;
 }
 
 // Resolve (s, D, NH): the caller's choice, else DKB_TUNING="s,D,NH", else the
@@ -148,31 +162,32 @@ int resolve_tuning(dkb_ctx *ctx, size_t n_entries, bool hints) {
     }
   }
   const int k = ctx->k;
-  if (t.stride != 0 && t.stride != 1 && t.stride != 2 && t.stride != 4)
-    return fail(ctx, DKB_EINVAL, "stride must be 1, 2 or 4");
+  if (t.stride != 0 && t.stride != 1 && t.stride != 2 && t.stride != 4 && t.stride != 8 &&
+      t.stride != 16)
+    return fail(ctx, DKB_EINVAL, "stride must be 1, 2, 4, 8 or 16");
   if (t.bloom_hashes < 0 || t.bloom_hashes > 4)
     return fail(ctx, DKB_EINVAL, "bloom_hashes must be 1..4");
-  int best_D = 0, best_NH = 0;
+  if (t.seed_len != 0 && (t.seed_len < 8 || t.seed_len > MAX_SEED_LEN))
+    return fail(ctx, DKB_EINVAL, "seed_len out of range (8..15 and <= k - stride + 1)");
+  int best_D = 0, best_NH = 0, best_s = 0;
   double best = 1e300;
-  for (int D = 1; D <= 4; D *= 2) {
+  for (int D = 1; D <= 16; D *= 2) {
     if (t.stride && t.stride != D) continue;
-    if (k - D + 1 < 8) continue;
-    for (int NH = 1; NH <= 2; NH++) {  // 3 and 4 never beat 2 in measurements; manual only
-      if (t.bloom_hashes && t.bloom_hashes != NH) continue;
-      const double c = tile_cost((double)n_entries, hints, k, D, NH);
-      if (c < best) { best = c; best_D = D; best_NH = NH; }
+    for (int s = 8; s <= MAX_SEED_LEN; s++) {
+      if (t.seed_len && t.seed_len != s) continue;
+      if (s > k - D + 1) continue;
+      for (int NH = 1; NH <= 4; NH++) {
+        if (t.bloom_hashes ? t.bloom_hashes != NH : NH > 2) continue;  // 3, 4: manual only
+        const double c = tile_cost((double)n_entries, hints, k, s, D, NH, nullptr);
+        if (c < best) { best = c; best_D = D; best_NH = NH; best_s = s; }
+      }
     }
   }
-  int D = t.stride ? t.stride : best_D;
-  int NH = t.bloom_hashes ? t.bloom_hashes : best_NH;
-  if (D == 0) return fail(ctx, DKB_EINVAL, "no stride fits this k");
-  if (NH == 0) NH = 2;
-  int s = t.seed_len ? t.seed_len : default_seed_len(k, D);
-  if (s < 8 || s > MAX_SEED_LEN || s > k - D + 1)
-    return fail(ctx, DKB_EINVAL, "seed_len out of range (8..15 and <= k - stride + 1)");
-  ctx->s = s;
-  ctx->D = D;
-  ctx->NH = NH;
+  if (best_D == 0)
+    return fail(ctx, DKB_EINVAL, "no (seed_len, stride) fits: need seed_len <= k - stride + 1");
+  ctx->s = best_s;
+  ctx->D = best_D;
+  ctx->NH = best_NH;
   return DKB_OK;
 }
 
@@ -217,7 +232,8 @@ scan_fn pick_scan(int D, int NH, bool prof) {
 #define PICK(d, h)                                                         \
   if (D == d && NH == h) return prof ? (scan_fn)k_scan<d, h, true> : (scan_fn)k_scan<d, h, false>;
   PICK(1, 1) PICK(1, 2) PICK(1, 3) PICK(1, 4) PICK(2, 1) PICK(2, 2) PICK(2, 3) PICK(2, 4)
-  PICK(4, 1) PICK(4, 2) PICK(4, 3) PICK(4, 4)
+  PICK(4, 1) PICK(4, 2) PICK(4, 3) PICK(4, 4) PICK(8, 1) PICK(8, 2) PICK(8, 3) PICK(8, 4)
+  PICK(16, 1) PICK(16, 2) PICK(16, 3) PICK(16, 4)
 #undef PICK
   return nullptr;
 }

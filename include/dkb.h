@@ -83,7 +83,7 @@ typedef struct dkb_thresholds {
 /* Scan tuning, normally left to the library (dkb_ctx_set_tuning(ctx, NULL)). */
 typedef struct dkb_tuning {
   int seed_len;     /* s: 8..15 and <= k - stride + 1; 0 = auto */
-  int stride;       /* D: probe every D-th stream position (1, 2 or 4); 0 = auto */
+  int stride;       /* D: probe every D-th stream position (1, 2, 4, 8 or 16); 0 = auto */
   int bloom_hashes; /* 1..4 bits per seed in the shared-memory filter; 0 = auto */
 } dkb_tuning;
 
