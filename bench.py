@@ -46,7 +46,10 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genome-mb", type=float, default=64.0, help="region size per GPU, Mb")
     ap.add_argument("--depth", type=float, default=30.0)
-    ap.add_argument("--variants", type=int, default=10000)
+    ap.add_argument("--variants", type=int, default=10000, help="candidates inside this GPU's region")
+    ap.add_argument("--table-variants", type=int, default=0,
+                    help="total candidates in the replicated table (>= --variants): the extra ones lie "
+                         "in other regions of a larger genome, as for one GPU's shard of a WGS job")
     ap.add_argument("--indel-frac", type=float, default=0.0)
     ap.add_argument("--k", type=int, default=31)
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -58,8 +61,9 @@ def parse_args():
 
 
 def workload_name(a):
+    extra = f" of {a.table_variants} in the table" if a.table_variants > a.variants else ""
     return (f"synthetic {a.depth:g}x trio, {a.genome_mb:g} Mb region per GPU, {READ_LEN} bp reads, "
-            f"{a.variants} candidate DNMs, k={a.k}")
+            f"{a.variants} candidate DNMs{extra}, k={a.k}")
 
 
 # ------------------------------------------------------------------------------------
@@ -70,8 +74,13 @@ def build_table_inputs(a):
     glen = int(a.genome_mb * 1e6)
     genome = synth.make_genome(glen, seed=1)
     variants = synth.plant_variants(genome, a.variants, a.k, seed=2, indel_frac=a.indel_frac)
-    trio = synth.Trio(a.k, genome, variants)
-    entries = dkb.variant_kmers(trio.variant_tuples(), a.k)
+    tuples = synth.Trio(a.k, genome, variants).variant_tuples()
+    extra = max(0, a.table_variants - a.variants)
+    if extra:  # candidates of other regions: same model, sequence this shard's reads never contain
+        other = synth.make_genome(max(int(extra * 400), 1_000_000), seed=7)
+        tuples += synth.Trio(a.k, other, synth.plant_variants(other, extra, a.k, seed=8,
+                                                              indel_frac=a.indel_frac)).variant_tuples()
+    entries = dkb.variant_kmers(tuples, a.k)
     return genome, variants, entries
 
 
@@ -228,10 +237,18 @@ def run_ours(a):
     counts_t = dist.counts_tensor(kc)
     ext = torch.cuda.ExternalStream(kc.scan_stream(), device=dev)
 
+    # one launch per <= 2^31 positions, cut after a multiple of 128 reads (word-aligned)
+    max_reads = (1 << 31) // (READ_LEN + 1) // 128 * 128
+
+    def submit_resident(s, b2, m1, n_pos):
+        per = max_reads * (READ_LEN + 1)
+        for p0 in range(0, n_pos, per):
+            kc.submit_device(b2.data_ptr() + p0 // 4, m1.data_ptr() + p0 // 8, min(per, n_pos - p0), s)
+
     def step():
         kc.reset_counts()
         for s, (b2, m1, n_pos, _) in enumerate(streams):
-            kc.submit_device(b2.data_ptr(), m1.data_ptr(), n_pos, s)
+            submit_resident(s, b2, m1, n_pos)
         if world > 1:
             with torch.cuda.stream(ext):
                 dist.allreduce_counts(counts_t)
@@ -271,7 +288,7 @@ def run_ours(a):
     # roofline of the scan kernel: bytes it must stream per launch / mean launch time
     launches = s1["scan_launches_timed"] - s0["scan_launches_timed"]
     scan_ms = (s1["scan_ms_total"] - s0["scan_ms_total"]) / max(launches, 1)
-    bytes_per_launch = stream_bytes / 3.0
+    bytes_per_launch = stream_bytes / max(launches / max(a.steps, 1), 1)
     peak, peak_src = measured_peak_gbs()
     achieved = bytes_per_launch / (scan_ms * 1e-3) / 1e9
     traffic = None
@@ -343,7 +360,7 @@ def run_ours(a):
                 "l2": "inputs larger than L2 (%.2f GB of packed streams per step per GPU)" % (
                     (stream_bytes + mask_bytes) / 1e9),
                 "table_entries": int(st["n_entries"]), "seeds": int(st["n_seeds"]),
-                "tuning_seedlen_stride_hashes": list(kc.tuning()),
+                "tuning_seedlen_stride_hashes_filtermode": list(kc.tuning()),
                 "denovo_calls": int((calls & 1).sum()), "variants": int(len(calls)),
                 "collective": "1 NCCL allreduce(sum) of %d uint32 per step" % counts_t.numel() if world > 1 else "none",
             },

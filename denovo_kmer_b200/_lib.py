@@ -21,7 +21,8 @@ class Thresholds(C.Structure):
 
 
 class Tuning(C.Structure):
-    _fields_ = [("seed_len", C.c_int), ("stride", C.c_int), ("bloom_hashes", C.c_int)]
+    _fields_ = [("seed_len", C.c_int), ("stride", C.c_int), ("bloom_hashes", C.c_int),
+                ("filter_mode", C.c_int)]
 
 
 class Stats(C.Structure):

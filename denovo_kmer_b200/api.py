@@ -153,14 +153,15 @@ class KmerCounter:
     def _ck(self, code):
         check(code, self._h)
 
-    def set_tuning(self, seed_len=0, stride=0, bloom_hashes=0):
-        t = Tuning(seed_len, stride, bloom_hashes)
+    def set_tuning(self, seed_len=0, stride=0, bloom_hashes=0, filter_mode=0):
+        """0 = auto for every field; filter_mode 1 = shared memory, 2 = L2."""
+        t = Tuning(seed_len, stride, bloom_hashes, filter_mode)
         self._ck(self._L.dkb_ctx_set_tuning(self._h, C.byref(t)))
 
     def tuning(self):
         t = Tuning()
         self._ck(self._L.dkb_ctx_get_tuning(self._h, C.byref(t)))
-        return t.seed_len, t.stride, t.bloom_hashes
+        return t.seed_len, t.stride, t.bloom_hashes, t.filter_mode
 
     def build_table(self, entries: KmerEntries, use_window_hints: bool = True):
         keys = np.ascontiguousarray(entries.keys, dtype=np.uint64)

@@ -23,8 +23,10 @@ struct dkb_ctx {
   int n_sms = 0;
   std::string err;
 
-  dkb_tuning user_tuning{0, 0, 0};
+  dkb_tuning user_tuning{0, 0, 0, 0};
   int s = 0, D = 0, NH = 0;  // resolved at table build
+  bool gf = false;           // seed filter probed in L2 instead of shared memory
+  uint32_t bloom_words = BLOOM_WORDS;
 
   // entries
   size_t n_entries = 0, n_live = 0;
@@ -115,6 +117,18 @@ void free_table(dkb_ctx *c) {
   c->finalised = false;
 }
 
+// Words of the L2-resident seed filter: 64 bits per seed, between the shared-memory size
+// and 16 MB (it shares L2 with the tables and the stream; DKB_L2_FILTER_MAX_WORDS overrides).
+uint32_t l2_filter_words(double seeds) {
+  double cap = 4.0 * 1024 * 1024;  // 16 MB: larger filters start missing L2 (measured, profiles/README.md)
+  if (const char *e = getenv("DKB_L2_FILTER_MAX_WORDS")) cap = atof(e);
+  double w = seeds * 2.0;
+  if (w > cap) w = cap;
+  if (w < BLOOM_WORDS) w = BLOOM_WORDS;
+  return (uint32_t)w;
+}
+constexpr double L2_LOOKUP_CYCLES = 450.0;  // per lane lookup, fitted (profiles/README.md)
+
 // Ladder seeds one SNV-sized haplotype strand needs (k windows) at stride D, seed length s.
 double ladder_seeds_per_strand(int k, int s, int D) {
   const int E = k - s, G = ((E + 1) / D) * D, nwin = k;
@@ -128,13 +142,14 @@ double ladder_seeds_per_strand(int k, int s, int D) {
 
 // Modelled cost of one 2048-position warp tile: filter lookups + handling of the filter's false positives +
 // stage C work for s-mers of unrelated sequence that equal a seed by chance.
-double tile_cost(double n_entries, bool hints, int k, int s, int D, int NH, double *seeds_out) {
+double tile_cost(double n_entries, bool hints, int k, int s, int D, int NH, bool gf,
+                 double *seeds_out) {
   const double n_haps = n_entries / k;  // allele haplotypes (SNV-sized)
   // both strands; ref/alt haplotypes share the seeds that avoid the variant base (x0.7)
   double seeds = n_haps * 2.0 * 0.7 * ladder_seeds_per_strand(k, s, D);
   if (!hints) seeds *= 2.3;  // min-hash rule: ~2/(w+1) density instead of 1/w
   if (seeds_out) *seeds_out = seeds;
-  const double bits = (double)BLOOM_WORDS * 32;
+  const double bits = 32.0 * (gf ? l2_filter_words(seeds) : (double)BLOOM_WORDS);
   const double dens = 1.0 - exp(-NH * seeds / bits);
   const double fp = pow(dens, NH) * 1.3 + 1e-4;  // 1.3: per-word load variance
   const double lookups_lane = 64.0 / D, lookups_tile = 2048.0 / D;
@@ -144,9 +159,12 @@ double tile_cost(double n_entries, bool hints, int k, int s, int D, int NH, doub
   // A filter lookup is bound by shared-memory wavefronts (bank conflicts), not by its ~8
   // instructions; the first 32 false positives of a tile ride the pipelined probe batch,
   // later ones wait for L2; a seed table beyond ~16 MB stops being L2-friendly.
-  const double per_hit = 4.4 * (seeds > 5e5 ? 1.6 : 1.0);
-  return 136.0 + lookups_lane * (29.0 + 2.0 * NH) + per_hit * (hits < 32 ? hits : 32) +
-         (hits > 32 ? 9.0 * (hits - 32) : 0.0) + 25.0 * lookups_tile * chance;
+  // seed-table probes: the table is 32 B per seed; beyond L2 every probe goes to DRAM
+  const double per_hit = 4.4 * (seeds > 2e6 ? 6.0 : seeds > 5e5 ? 1.6 : 1.0);
+  // a lookup in the L2-resident filter is a fully divergent global load: 32 L1 wavefronts
+  const double per_lookup = gf ? L2_LOOKUP_CYCLES : 29.0 + 2.0 * NH;
+  return 136.0 + lookups_lane * per_lookup + per_hit * (hits < 32 ? hits : 32) +
+         (hits > 32 ? 2.0 * per_hit * (hits - 32) : 0.0) + 140.0 * lookups_tile * chance;
 }
 
 // Resolve (s, D, NH): the caller's choice, else DKB_TUNING="s,D,NH", else the
@@ -154,11 +172,12 @@ double tile_cost(double n_entries, bool hints, int k, int s, int D, int NH, doub
 int resolve_tuning(dkb_ctx *ctx, size_t n_entries, bool hints) {
   dkb_tuning t = ctx->user_tuning;
   if (const char *e = getenv("DKB_TUNING")) {
-    int a = 0, b = 0, c = 0;
-    if (sscanf(e, "%d,%d,%d", &a, &b, &c) >= 1) {
+    int a = 0, b = 0, c = 0, d = 0;
+    if (sscanf(e, "%d,%d,%d,%d", &a, &b, &c, &d) >= 1) {
       if (!t.seed_len) t.seed_len = a;
       if (!t.stride) t.stride = b;
       if (!t.bloom_hashes) t.bloom_hashes = c;
+      if (!t.filter_mode) t.filter_mode = d;
     }
   }
   const int k = ctx->k;
@@ -169,25 +188,35 @@ int resolve_tuning(dkb_ctx *ctx, size_t n_entries, bool hints) {
     return fail(ctx, DKB_EINVAL, "bloom_hashes must be 1..4");
   if (t.seed_len != 0 && (t.seed_len < 8 || t.seed_len > MAX_SEED_LEN))
     return fail(ctx, DKB_EINVAL, "seed_len out of range (8..15 and <= k - stride + 1)");
-  int best_D = 0, best_NH = 0, best_s = 0;
+  if (t.filter_mode < 0 || t.filter_mode > 2)
+    return fail(ctx, DKB_EINVAL, "filter_mode must be 0 (auto), 1 (shared memory) or 2 (L2)");
+  int best_D = 0, best_NH = 0, best_s = 0, best_gf = 0;
   double best = 1e300;
-  for (int D = 1; D <= 16; D *= 2) {
-    if (t.stride && t.stride != D) continue;
-    for (int s = 8; s <= MAX_SEED_LEN; s++) {
-      if (t.seed_len && t.seed_len != s) continue;
-      if (s > k - D + 1) continue;
-      for (int NH = 1; NH <= 4; NH++) {
-        if (t.bloom_hashes ? t.bloom_hashes != NH : NH > 2) continue;  // 3, 4: manual only
-        const double c = tile_cost((double)n_entries, hints, k, s, D, NH, nullptr);
-        if (c < best) { best = c; best_D = D; best_NH = NH; best_s = s; }
+  for (int gf = 0; gf <= 1; gf++) {
+    if (t.filter_mode && t.filter_mode != gf + 1) continue;
+    for (int D = 1; D <= 16; D *= 2) {
+      if (t.stride && t.stride != D) continue;
+      if (gf && D < 2) continue;  // the L2 mode is built for strides 2..16
+      for (int s = 8; s <= MAX_SEED_LEN; s++) {
+        if (t.seed_len && t.seed_len != s) continue;
+        if (s > k - D + 1) continue;
+        for (int NH = 1; NH <= 4; NH++) {
+          if (gf && NH > 2) continue;
+          if (t.bloom_hashes ? t.bloom_hashes != NH : NH > 2) continue;  // 3, 4: manual only
+          const double c = tile_cost((double)n_entries, hints, k, s, D, NH, gf != 0, nullptr);
+          if (c < best) { best = c; best_D = D; best_NH = NH; best_s = s; best_gf = gf; }
+        }
       }
     }
   }
   if (best_D == 0)
-    return fail(ctx, DKB_EINVAL, "no (seed_len, stride) fits: need seed_len <= k - stride + 1");
+    return fail(ctx, DKB_EINVAL,
+                "no (seed_len, stride, hashes, filter_mode) fits: need seed_len <= k - stride + 1; "
+                "L2 mode takes strides 2..16 and 1..2 hashes");
   ctx->s = best_s;
   ctx->D = best_D;
   ctx->NH = best_NH;
+  ctx->gf = best_gf != 0;
   return DKB_OK;
 }
 
@@ -228,9 +257,16 @@ KeyTable key_table(const dkb_ctx *ctx) {
 
 typedef void (*scan_fn)(const ScanParams);
 
-scan_fn pick_scan(int D, int NH, bool prof) {
-#define PICK(d, h)                                                         \
-  if (D == d && NH == h) return prof ? (scan_fn)k_scan<d, h, true> : (scan_fn)k_scan<d, h, false>;
+scan_fn pick_scan(int D, int NH, bool gf, bool prof) {
+#define PICKG(d, h)                                                                     \
+  if (gf && D == d && NH == h)                                                          \
+    return prof ? (scan_fn)k_scan<d, h, true, true> : (scan_fn)k_scan<d, h, true, false>;
+  PICKG(2, 1) PICKG(2, 2) PICKG(4, 1) PICKG(4, 2) PICKG(8, 1) PICKG(8, 2) PICKG(16, 1) PICKG(16, 2)
+#undef PICKG
+  if (gf) return nullptr;
+#define PICK(d, h)              \
+  if (D == d && NH == h)        \
+    return prof ? (scan_fn)k_scan<d, h, false, true> : (scan_fn)k_scan<d, h, false, false>;
   PICK(1, 1) PICK(1, 2) PICK(1, 3) PICK(1, 4) PICK(2, 1) PICK(2, 2) PICK(2, 3) PICK(2, 4)
   PICK(4, 1) PICK(4, 2) PICK(4, 3) PICK(4, 4) PICK(8, 1) PICK(8, 2) PICK(8, 3) PICK(8, 4)
   PICK(16, 1) PICK(16, 2) PICK(16, 3) PICK(16, 4)
@@ -248,6 +284,7 @@ int launch_scan(dkb_ctx *ctx, const uint32_t *d_bases, const uint32_t *d_mask,
   P.n_mwords = (uint32_t)dkb_stream_mask_words(n_positions);
   P.n_tiles = (uint32_t)((n_positions + WTILE - 1) / WTILE);
   P.bloom = ctx->d_bloom;
+  P.bloom_words = ctx->bloom_words;
   P.st = seed_table(ctx);
   P.kt = key_table(ctx);
   P.seed_mult = SEED_MULT << (32 - 2 * ctx->s);
@@ -257,10 +294,10 @@ int launch_scan(dkb_ctx *ctx, const uint32_t *d_bases, const uint32_t *d_mask,
   P.k = ctx->k;
   P.s = ctx->s;
   P.prof = ctx->d_prof;
-  scan_fn fn = pick_scan(ctx->D, ctx->NH, ctx->prof);
+  scan_fn fn = pick_scan(ctx->D, ctx->NH, ctx->gf, ctx->prof);
   if (!fn) return fail(ctx, DKB_EINVAL, "no scan kernel for this tuning");
   CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)SCAN_SMEM_BYTES));
+                          (int)SCAN_SMEM_BYTES));  // same carve-out in both filter modes
   uint32_t grid = (P.n_tiles + SCAN_WARPS - 1) / SCAN_WARPS;
   if (grid > (uint32_t)ctx->n_sms) grid = ctx->n_sms;
   if (grid == 0) return DKB_OK;
@@ -373,7 +410,7 @@ int dkb_ctx_destroy(dkb_ctx *ctx) {
 
 int dkb_ctx_set_tuning(dkb_ctx *ctx, const dkb_tuning *tuning) {
   if (!ctx) return fail(nullptr, DKB_EINVAL, "ctx is null");
-  ctx->user_tuning = tuning ? *tuning : dkb_tuning{0, 0, 0};
+  ctx->user_tuning = tuning ? *tuning : dkb_tuning{0, 0, 0, 0};
   return DKB_OK;
 }
 
@@ -382,6 +419,7 @@ int dkb_ctx_get_tuning(const dkb_ctx *ctx, dkb_tuning *out) {
   out->seed_len = ctx->s;
   out->stride = ctx->D;
   out->bloom_hashes = ctx->NH;
+  out->filter_mode = ctx->gf ? 2 : 1;
   return DKB_OK;
 }
 
@@ -425,7 +463,6 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
     CU(cudaMalloc(&ctx->d_dead, n1));
     CU(cudaMalloc(&d_slot_of, n1 * 4));
     CU(cudaMalloc(&ctx->d_tslots, (size_t)ctx->table_slots * 16));
-    CU(cudaMalloc(&ctx->d_bloom, (size_t)BLOOM_WORDS * 4));
     CU(cudaMalloc(&ctx->d_counts, n1 * 3 * 4));
     CU(cudaMalloc(&ctx->d_hits, nv1 * 6 * 4));
     CU(cudaMalloc(&ctx->d_distinct, nv1 * 6 * 4));
@@ -433,7 +470,6 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
     CU(cudaMalloc(&ctx->d_calls, nv1));
     CU(cudaMalloc(&d_nseeds, 4));
     CU(cudaMemsetAsync(ctx->d_tslots, 0xFF, (size_t)ctx->table_slots * 16, st));
-    CU(cudaMemsetAsync(ctx->d_bloom, 0, (size_t)BLOOM_WORDS * 4, st));
     CU(cudaMemsetAsync(ctx->d_counts, 0, n1 * 3 * 4, st));
     CU(cudaMemsetAsync(ctx->d_dead, 0, n1, st));
     CU(cudaMemsetAsync(d_nseeds, 0, 4, st));
@@ -465,7 +501,7 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
       k_mark_repeats<<<g1, TB, 0, st>>>(B);
       k_apply_dead<<<g1, TB, 0, st>>>(B);
       k_assign_seeds<<<g2, TB, 0, st>>>(B, true, d_set, set_slots - 1, d_nseeds, SeedTable{},
-                                        nullptr, seed_mult, ctx->NH);
+                                        nullptr, 0, seed_mult, ctx->NH);
       CU(cudaGetLastError());
     }
     unsigned int n_seeds = 0;
@@ -478,14 +514,17 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
     CU(cudaMalloc(&ctx->d_sinfo, (size_t)ctx->seed_slots * 4));
     CU(cudaMemsetAsync(ctx->d_seeds, 0xFF, (size_t)ctx->seed_slots * 4, st));
     CU(cudaMemsetAsync(ctx->d_sinfo, 0, (size_t)ctx->seed_slots * 4, st));
+    ctx->bloom_words = ctx->gf ? l2_filter_words((double)n_seeds) / 4 * 4 : (uint32_t)BLOOM_WORDS;
+    CU(cudaMalloc(&ctx->d_bloom, (size_t)ctx->bloom_words * 4));
+    CU(cudaMemsetAsync(ctx->d_bloom, 0, (size_t)ctx->bloom_words * 4, st));
     if (n) {
       k_assign_seeds<<<g2, TB, 0, st>>>(B, false, nullptr, 0, nullptr, seed_table(ctx),
-                                        ctx->d_bloom, seed_mult, ctx->NH);
+                                        ctx->d_bloom, ctx->bloom_words, seed_mult, ctx->NH);
       CU(cudaGetLastError());
     }
-    std::vector<uint32_t> bloom(BLOOM_WORDS);
+    std::vector<uint32_t> bloom(ctx->bloom_words);
     std::vector<uint8_t> dead(n1);
-    CU(cudaMemcpyAsync(bloom.data(), ctx->d_bloom, (size_t)BLOOM_WORDS * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(bloom.data(), ctx->d_bloom, (size_t)ctx->bloom_words * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(dead.data(), ctx->d_dead, n1, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     ctx->bloom_bits_set = 0;
@@ -631,7 +670,7 @@ int dkb_stats_get(dkb_ctx *ctx, dkb_stats *out) {
   out->table_slots = ctx->table_slots;
   out->n_seeds = ctx->n_seeds;
   out->seed_slots = ctx->seed_slots;
-  out->bloom_words = BLOOM_WORDS;
+  out->bloom_words = ctx->bloom_words;
   out->bloom_bits_set = ctx->bloom_bits_set;
   out->scan_launches = ctx->scan_launches;
   out->positions_scanned = ctx->positions_scanned;

@@ -118,7 +118,8 @@ __device__ __forceinline__ void seedset_insert(uint32_t *set, uint32_t mask, uin
 // offsets in the entry's slot, insert the seeds and set their filter bits.
 __global__ void k_assign_seeds(const BuildParams B, bool count_only, uint32_t *set,
                                uint32_t set_mask, unsigned int *n_seeds, const SeedTable T,
-                               uint32_t *bloom, uint32_t seed_mult, int n_hashes) {
+                               uint32_t *bloom, uint32_t bloom_words, uint32_t seed_mult,
+                               int n_hashes) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t i = t >> 1;
   const int ori = t & 1;
@@ -169,7 +170,7 @@ __global__ void k_assign_seeds(const BuildParams B, bool count_only, uint32_t *s
       offs |= (uint32_t)(j / D) << (W * (ori * D + c));
       seedtab_insert(T, seed, 1u << j);
       const uint32_t h = seed * seed_mult;
-      atomicOr(bloom + __umulhi(h, (uint32_t)BLOOM_WORDS), bloom_bits(seed, h, n_hashes));
+      atomicOr(bloom + __umulhi(h, bloom_words), bloom_bits(seed, h, n_hashes));
     }
   }
   if (!count_only) atomicOr(&B.kt.slots[B.slot_of[i]].w, offs);

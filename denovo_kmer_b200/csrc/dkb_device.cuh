@@ -145,7 +145,9 @@ struct ScanParams {
   const uint32_t *bases;  // 2-bit stream, 16 positions per word
   const uint32_t *mask;   // 1-bit validity stream, 32 positions per word
   uint32_t n_pos, n_bwords, n_mwords, n_tiles;
-  const uint32_t *bloom;  // BLOOM_WORDS words, copied into shared memory per CTA
+  const uint32_t *bloom;  // seed filter: BLOOM_WORDS words copied into shared memory per CTA,
+                          // or (large candidate sets) bloom_words words probed in L2
+  uint32_t bloom_words;
   SeedTable st;
   KeyTable kt;
   uint32_t seed_mult;  // SEED_MULT << (32 - 2s): the product ignores bases beyond s

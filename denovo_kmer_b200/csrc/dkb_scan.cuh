@@ -17,7 +17,7 @@
 
 namespace dkb {
 
-template <int D, int NH, bool PROF>
+template <int D, int NH, bool GF, bool PROF>
 struct ScanWarp {
   const ScanParams &P;
   const uint32_t *filt;
@@ -254,10 +254,15 @@ struct ScanWarp {
       for (int t = 0; t < 16; t += D) {
         const uint32_t x = t ? __funnelshift_r(w[c], w[c + 1], 2 * t) : w[c];
         const uint32_t h = x * mult;
-        // byte address = idx * 4 + base as a multiply-add (P.four is opaque), not an ALU-pipe LEA
-        const uint32_t addr = __umulhi(h, (uint32_t)BLOOM_WORDS) * P.four + fbase;
         uint32_t word;
-        asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(addr));
+        if constexpr (GF) {
+          // large candidate sets: the filter does not fit in shared memory; probe it in L2
+          word = ldg_u32_hint(P.bloom + __umulhi(h, P.bloom_words), keep);
+        } else {
+          // byte address = idx * 4 + base as a multiply-add (P.four is opaque), not an ALU-pipe LEA
+          const uint32_t addr = __umulhi(h, (uint32_t)BLOOM_WORDS) * P.four + fbase;
+          asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(addr));
+        }
         uint32_t bit = word << (x & 31);
         if (NH >= 2) bit &= word << (__umulhi(h, SEED_MULT2) & 31);
         if (NH >= 3) bit &= word << (__umulhi(h, SEED_MULT3) & 31);
@@ -302,19 +307,21 @@ __device__ __forceinline__ void halo_finish(int lane, uint32_t (&w)[5]) {
   if (lane != 31) w[4] = up;
 }
 
-template <int D, int NH, bool PROF>
+template <int D, int NH, bool GF, bool PROF>
 __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t *filt = smem;
   uint64_t *cq_all = reinterpret_cast<uint64_t *>(smem + BLOOM_WORDS);
   uint16_t *hl_all = reinterpret_cast<uint16_t *>(cq_all + SCAN_WARPS * CQ_CAP);
 
-  for (int i = threadIdx.x; i < BLOOM_WORDS / 4; i += SCAN_THREADS)
-    reinterpret_cast<uint4 *>(filt)[i] = __ldg(reinterpret_cast<const uint4 *>(P.bloom) + i);
-  __syncthreads();
+  if constexpr (!GF) {
+    for (int i = threadIdx.x; i < BLOOM_WORDS / 4; i += SCAN_THREADS)
+      reinterpret_cast<uint4 *>(filt)[i] = __ldg(reinterpret_cast<const uint4 *>(P.bloom) + i);
+    __syncthreads();
+  }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  ScanWarp<D, NH, PROF> W(P, filt, hl_all + warp * HL_CAP, cq_all + warp * CQ_CAP, lane);
+  ScanWarp<D, NH, GF, PROF> W(P, filt, hl_all + warp * HL_CAP, cq_all + warp * CQ_CAP, lane);
 
   const uint32_t n_warps = gridDim.x * SCAN_WARPS;
   uint32_t tile = blockIdx.x * SCAN_WARPS + warp;

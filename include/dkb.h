@@ -84,7 +84,9 @@ typedef struct dkb_thresholds {
 typedef struct dkb_tuning {
   int seed_len;     /* s: 8..15 and <= k - stride + 1; 0 = auto */
   int stride;       /* D: probe every D-th stream position (1, 2, 4, 8 or 16); 0 = auto */
-  int bloom_hashes; /* 1..4 bits per seed in the shared-memory filter; 0 = auto */
+  int bloom_hashes; /* 1..4 bits per seed in the seed filter; 0 = auto */
+  int filter_mode;  /* 1 = filter in shared memory, 2 = filter in L2 (large candidate sets:
+                       strides 2..16, 1..2 hashes); 0 = auto */
 } dkb_tuning;
 
 /* ---- library ---------------------------------------------------------- */

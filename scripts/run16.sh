@@ -3,5 +3,5 @@ timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 for args in "" "--variants 100 --genome-mb 16"; do
 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline $args 2>&1 | tail -1 | python -c "
 import sys,json
-d=json.loads(sys.stdin.readline()); print('$args value %.3f T/s' % (d['value']/1e12), 'scan_ms %.3f' % d['roofline']['launch_ms'], d['config']['tuning_seedlen_stride_hashes'], 'frac %.3f' % d['roofline']['frac'])"
+d=json.loads(sys.stdin.readline()); print('$args value %.3f T/s' % (d['value']/1e12), 'scan_ms %.3f' % d['roofline']['launch_ms'], d['config']['tuning_seedlen_stride_hashes_filtermode'], 'frac %.3f' % d['roofline']['frac'])"
 done

@@ -63,7 +63,7 @@ def test_reads_shorter_than_k_and_all_masked(dkb, orc):
     assert got[0].sum() == 0 and got[1].sum() == 0 and got[2].sum() > 0
 
 
-@pytest.mark.parametrize("tuning", [None, (15, 1, 1), (15, 2, 2), (14, 4, 2), (8, 4, 1), (12, 8, 2)])
+@pytest.mark.parametrize("tuning", [None, (15, 1, 1), (15, 2, 2), (14, 4, 2), (8, 4, 1), (12, 8, 2), (12, 4, 2, 2)])
 def test_low_complexity_dense_hits(dkb, orc, tuning):
     """Poly-A / dinucleotide / short tandem repeats: the same seed recurs at every position,
     filter hits exceed the per-tile id list, keys repeat inside one allele."""

@@ -70,7 +70,7 @@ def test_split_additivity_and_tuning_invariance(dkb):
     stride = RL + 1
     results = {}
     for tuning in [None, (15, 1, 1), (15, 1, 2), (15, 2, 1), (15, 2, 2), (14, 4, 1), (14, 4, 2),
-                   (14, 4, 3), (12, 2, 4), (9, 1, 1), (15, 8, 2), (15, 16, 1), (12, 16, 2)]:
+                   (14, 4, 3), (12, 2, 4), (9, 1, 1), (15, 8, 2), (15, 16, 1), (12, 16, 2), (15, 16, 2, 2), (14, 4, 2, 2)]:
         with dkb.KmerCounter(K, tuning=tuning) as kc:
             kc.build_table(entries)
             for s, (b2, m1, n_pos, _) in enumerate(streams):

@@ -22,7 +22,7 @@ def _check(dkb, orc, trio, k, min_bq=20, drop_shared=True, **kw):
 
 @pytest.mark.parametrize("tuning", [None, (15, 1, 1), (15, 1, 2), (13, 1, 2), (15, 2, 1), (15, 2, 2),
                                     (14, 4, 1), (14, 4, 2), (12, 1, 1), (9, 2, 1), (15, 8, 2), (13, 8, 1), (15, 16, 2),
-                                    (9, 16, 1)])
+                                    (9, 16, 1), (15, 16, 2, 2), (14, 4, 1, 2), (15, 2, 2, 2), (13, 8, 2, 2)])
 @pytest.mark.parametrize("hints", [True, False])
 def test_snv_trio_k31(dkb, orc, tuning, hints):
     trio = synth.make_trio_host(200_000, 12, 40, 31, seed=5)
