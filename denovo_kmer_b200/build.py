@@ -9,7 +9,7 @@ DEPS = SRC + [os.path.join(_HERE, "csrc", f) for f in
     os.path.join(_HERE, "..", "include", "dkb.h")]
 OUT = os.path.join(_HERE, "libdkb.so")
 NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-O3", "-lineinfo",
-              "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "g++"]
+              "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "g++", "-Xcompiler", "-pthread"]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -71,28 +72,96 @@ uint64_t dkb_stream_positions(const uint64_t *offsets, size_t n_reads) {
 size_t dkb_stream_bases_words(uint64_t n_positions) { return (size_t)((n_positions + 63) / 64 * 4); }
 size_t dkb_stream_mask_words(uint64_t n_positions) { return (size_t)((n_positions + 127) / 128 * 4); }
 
+// Pack stream positions [p0, p1) (p0 a multiple of 32, so no output word is shared
+// between two calls).  Position of read r's first base: offsets[r] - offsets[0] + r.
+static void pack_range(const uint8_t *seq, const uint8_t *qual, const uint64_t *offsets,
+                       size_t n_reads, int min_baseq, uint32_t *bases2, uint32_t *mask1,
+                       uint64_t p0, uint64_t p1) {
+  const uint64_t o0 = offsets[0];
+  // last read whose first position is <= p0
+  size_t lo = 0, hi = n_reads;
+  while (hi - lo > 1) {
+    const size_t mid = (lo + hi) / 2;
+    if (offsets[mid] - o0 + mid <= p0) lo = mid; else hi = mid;
+  }
+  // words are built in registers and stored once (the range owns them exclusively)
+  uint64_t p = p0;
+  uint32_t cur_b = 0, cur_m = 0;
+  auto advance = [&](uint64_t to) {  // move to position `to`, flushing completed words
+    while ((p >> 4) != (to >> 4)) {
+      bases2[p >> 4] = cur_b;
+      cur_b = 0;
+      p = ((p >> 4) + 1) << 4;
+      if ((p & 31) == 0) {
+        mask1[(p >> 5) - 1] = cur_m;
+        cur_m = 0;
+      }
+    }
+    p = to;
+  };
+  for (size_t r = lo; r < n_reads && p < p1; r++) {
+    const uint64_t start = offsets[r] - o0 + r;  // stream position of the read's first base
+    const uint64_t len = offsets[r + 1] - offsets[r];
+    uint64_t i = p > start ? p - start : 0;       // first base of this read inside the range
+    if (start + i > p) advance(start + i < p1 ? start + i : p1);
+    if (p >= p1) break;
+    const uint8_t *sp = seq + offsets[r];
+    const uint8_t *qp = qual ? qual + offsets[r] : nullptr;
+    const uint64_t end = start + len < p1 ? len : p1 - start;  // bases of this read in range
+    for (; i < end; i++) {
+      const uint32_t c = LUT.t[sp[i]];
+      const uint32_t ok = (c <= 3) & (!qp || (int)qp[i] >= min_baseq);
+      const uint32_t sh = (uint32_t)(p & 15);
+      cur_b |= (ok ? c : 0u) << (2 * sh);
+      cur_m |= ok << (p & 31);
+      p++;
+      if (sh == 15) {
+        bases2[(p >> 4) - 1] = cur_b;
+        cur_b = 0;
+        if ((p & 31) == 0) {
+          mask1[(p >> 5) - 1] = cur_m;
+          cur_m = 0;
+        }
+      }
+    }
+    if (i == len) advance(start + len + 1 < p1 ? start + len + 1 : p1);  // the separator (flag 0)
+  }
+  advance(p1);
+  // p1 is either a multiple of 128 (all words flushed) or the end of the stream
+  if (p1 & 15) bases2[p1 >> 4] = cur_b;
+  if (p1 & 31) mask1[p1 >> 5] = cur_m;
+}
+
 int dkb_pack_reads(const uint8_t *seq, const uint8_t *qual, const uint64_t *offsets,
                    size_t n_reads, int min_baseq, uint32_t *bases2, uint32_t *mask1,
                    uint64_t *n_positions_out) {
   if (!offsets && n_reads) return DKB_EINVAL;
   if (!bases2 || !mask1) return DKB_EINVAL;
+  if (n_reads && !seq) return DKB_EINVAL;
+  for (size_t r = 0; r < n_reads; r++)
+    if (offsets[r + 1] < offsets[r]) return DKB_EINVAL;
   const uint64_t n_pos = dkb_stream_positions(offsets, n_reads);
   const size_t bw = dkb_stream_bases_words(n_pos), mw = dkb_stream_mask_words(n_pos);
-  memset(bases2, 0, bw * 4);
-  memset(mask1, 0, mw * 4);
-  uint64_t p = 0;
-  for (size_t r = 0; r < n_reads; r++) {
-    if (offsets[r + 1] < offsets[r]) return DKB_EINVAL;
-    const uint8_t *s = seq + offsets[r];
-    const uint8_t *q = qual ? qual + offsets[r] : nullptr;
-    const size_t len = (size_t)(offsets[r + 1] - offsets[r]);
-    for (size_t i = 0; i < len; i++, p++) {
-      const uint8_t c = LUT.t[s[i]];
-      if (c > 3 || (q && (int)q[i] < min_baseq)) continue;  // flag stays 0, base stays A
-      bases2[p >> 4] |= (uint32_t)c << (2 * (p & 15));
-      mask1[p >> 5] |= 1u << (p & 31);
-    }
-    p++;  // separator: flag 0
+  // output words are split between threads on 128-position boundaries: no sharing
+  unsigned n_thr = std::thread::hardware_concurrency();
+  if (n_thr > 32) n_thr = 32;
+  if (n_thr < 1 || n_pos < (1u << 20)) n_thr = 1;
+  const uint64_t per = ((n_pos + n_thr - 1) / n_thr + 127) / 128 * 128;
+  auto work = [&](unsigned t) {
+    const uint64_t p0 = (uint64_t)t * per, p1 = p0 + per < n_pos ? p0 + per : n_pos;
+    // this thread's words (the tail thread also clears the padding words)
+    const size_t b0 = (size_t)(p0 / 16), b1 = t + 1 == n_thr ? bw : (size_t)((p0 + per) / 16);
+    const size_t m0 = (size_t)(p0 / 32), m1 = t + 1 == n_thr ? mw : (size_t)((p0 + per) / 32);
+    if (b0 < bw) memset(bases2 + b0, 0, ((b1 < bw ? b1 : bw) - b0) * 4);
+    if (m0 < mw) memset(mask1 + m0, 0, ((m1 < mw ? m1 : mw) - m0) * 4);
+    if (p0 < p1 && n_reads) pack_range(seq, qual, offsets, n_reads, min_baseq, bases2, mask1, p0, p1);
+  };
+  if (n_thr == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < n_thr; t++) pool.emplace_back(work, t);
+    for (auto &th : pool) th.join();
   }
   if (n_positions_out) *n_positions_out = n_pos;
   return DKB_OK;

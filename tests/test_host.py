@@ -136,3 +136,32 @@ def test_argument_validation(dkb):
     arr = (C.c_char_p * 1)(b"A")
     assert L.dkb_variant_kmers(arr, arr, arr, arr, 1, 40, 1, None, None, None, None, None,
                                C.byref(n)) == _lib.EINVAL
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_pack_reads_threaded_large(dkb, ragged):
+    """Streams above 1 M positions are packed by several threads on 128-position cuts;
+    compare every position with a NumPy restatement (fixed and ragged read lengths)."""
+    from denovo_kmer_b200 import synth
+    g = synth.make_genome(300_000, 9)
+    seq, qual, off = synth.sample_reads([g], 30_000 if ragged else 12_000, 150, 3, ragged=ragged,
+                                        n_rate=0.01, lowq_frac=0.1)
+    st = dkb.pack_reads(seq, qual, off, 20)
+    assert st.n_positions > (1 << 20)
+    lut = np.full(256, 4, np.uint8)
+    for i, ch in enumerate(b"ACGT"):
+        lut[ch] = i
+    lens = np.diff(off).astype(np.int64)
+    pos = np.arange(len(seq)) + np.repeat(np.arange(len(off) - 1), lens)
+    c = lut[seq]
+    ok = (c < 4) & (qual >= 20)
+    exp_c = np.zeros(st.n_positions, np.uint8)
+    exp_f = np.zeros(st.n_positions, np.uint8)
+    exp_c[pos] = np.where(ok, c, 0)
+    exp_f[pos] = ok
+    p = np.arange(st.n_positions)
+    got_c = (st.bases2[p >> 4] >> (2 * (p & 15)).astype(np.uint32)) & 3
+    got_f = (st.mask1[p >> 5] >> (p & 31).astype(np.uint32)) & 1
+    assert np.array_equal(got_c, exp_c) and np.array_equal(got_f, exp_f)
+    assert st.bases2[(st.n_positions + 15) // 16:].sum() == 0
+    assert st.mask1[(st.n_positions + 31) // 32:].sum() == 0
