@@ -161,3 +161,38 @@ def test_state_errors(dkb):
             kc.results()  # finalise has not run
         with pytest.raises(dkb.DkbError):
             kc.set_tuning(16, 1, 1) or kc.build_table(ent)  # seed_len 16 is outside 8..15
+
+
+def test_context_lifecycle(dkb, orc):
+    """Rebuild the table inside one context, run two contexts side by side, reset counters:
+    each result must still equal the oracle's."""
+    trio_a = synth.make_trio_host(30_000, 10, 8, 31, seed=51)
+    trio_b = synth.make_trio_host(30_000, 10, 8, 21, seed=52, indel_frac=0.5)
+    ent_a = dkb.variant_kmers(trio_a.variant_tuples(), 31)
+    ent_b31 = dkb.variant_kmers(trio_b.variant_tuples(), 31)
+    ent_b = dkb.variant_kmers(trio_b.variant_tuples(), 21)
+
+    def want(ent, trio, k):
+        ks = orc.KmerSet(ent.keys, ent.variant, ent.allele)
+        return ks.count_reads(*trio.reads[0], k, 20)
+
+    with dkb.KmerCounter(31) as k1, dkb.KmerCounter(21) as k2:
+        k1.build_table(ent_a)
+        k2.build_table(ent_b)
+        k1.submit(dkb.pack_reads(*trio_a.reads[0], 20), 0)
+        k2.submit(dkb.pack_reads(*trio_b.reads[0], 20), 0)
+        assert np.array_equal(k1.entry_counts()[0].astype(np.uint64), want(ent_a, trio_a, 31))
+        assert np.array_equal(k2.entry_counts()[0].astype(np.uint64), want(ent_b, trio_b, 21))
+        # counters accumulate across submits until reset
+        k1.submit(dkb.pack_reads(*trio_a.reads[0], 20), 0)
+        assert np.array_equal(k1.entry_counts()[0].astype(np.uint64), 2 * want(ent_a, trio_a, 31))
+        k1.reset_counts()
+        assert k1.entry_counts().sum() == 0
+        # a second build in the same context replaces table, seeds, filter and counters
+        k1.set_tuning(15, 2, 2)
+        k1.build_table(ent_b31)
+        k1.submit(dkb.pack_reads(*trio_b.reads[0], 20), 0)
+        assert np.array_equal(k1.entry_counts()[0].astype(np.uint64), want(ent_b31, trio_b, 31))
+        assert k1.tuning()[:3] == (15, 2, 2)
+        st = k1.stats()
+        assert st["n_entries"] == len(ent_b31) and st["scan_launches"] == 3

@@ -165,3 +165,44 @@ def test_pack_reads_threaded_large(dkb, ragged):
     assert np.array_equal(got_c, exp_c) and np.array_equal(got_f, exp_f)
     assert st.bases2[(st.n_positions + 15) // 16:].sum() == 0
     assert st.mask1[(st.n_positions + 31) // 32:].sum() == 0
+
+
+def test_header_is_plain_c_and_links(dkb, tmp_path):
+    """include/dkb.h must compile as C11 and a C program must link against libdkb.so and
+    call the host-side entry points (the boundary is a C ABI, not a C++ one)."""
+    import subprocess
+    from denovo_kmer_b200 import _lib
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "dkb.h"
+int main(void) {
+  uint64_t f = 0;
+  if (dkb_abi_version() != DKB_ABI_VERSION) return 1;
+  if (dkb_kmer_encode("ACGTT", 5, &f) != DKB_OK || f != 111) return 2;
+  if (dkb_kmer_canonical(f, 5) != 27 || dkb_kmer_revcomp(f, 5) != 27) return 3;
+  const uint8_t seq[] = "ACGTNACGTAC";
+  const uint64_t off[3] = {0, 5, 11};
+  uint32_t b[4], m[4];
+  uint64_t n = 0;
+  if (dkb_pack_reads(seq, NULL, off, 2, 0, b, m, &n) != DKB_OK || n != 13) return 4;
+  if (m[0] != 0xFCFu) return 5;
+  dkb_ctx *ctx = NULL;
+  int rc = dkb_ctx_create(0, 40, &ctx);
+  if (rc != DKB_EINVAL || ctx != NULL) return 6;
+  dkb_thresholds t = {3, 2, 0, 1};
+  dkb_tuning tu = {0, 0, 0, 0};
+  (void)t; (void)tu;
+  printf("%s\n", dkb_strerror(DKB_ENODEV));
+  return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.dirname(_lib.SO_PATH)
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", inc, str(src), "-o", str(exe),
+                           "-L", libdir, "-ldkb", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "no usable CUDA device" in out.stdout
