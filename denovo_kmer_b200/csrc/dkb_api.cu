@@ -155,16 +155,23 @@ double tile_cost(double n_entries, bool hints, int k, int s, int D, int NH, bool
   const double lookups_lane = 64.0 / D, lookups_tile = 2048.0 / D;
   const double hits = lookups_tile * fp;
   const double chance = seeds / pow(4.0, s);  // P(random s-mer is a seed)
-  // Cycles per warp tile and scheduler, fitted to measured scan times (profiles/README.md).
-  // A filter lookup is bound by shared-memory wavefronts (bank conflicts), not by its ~8
-  // instructions; the first 32 false positives of a tile ride the pipelined probe batch,
-  // later ones wait for L2; a seed table beyond ~16 MB stops being L2-friendly.
-  // seed-table probes: the table is 32 B per seed; beyond L2 every probe goes to DRAM
-  const double per_hit = 4.4 * (seeds > 2e6 ? 6.0 : seeds > 5e5 ? 1.6 : 1.0);
-  // a lookup in the L2-resident filter is a fully divergent global load: 32 L1 wavefronts
+  // Cycles per 2048-position warp tile and scheduler, fitted to measured scan times
+  // (profiles/README.md).  A shared-memory lookup is bound by bank-conflict wavefronts, not
+  // by its ~8 instructions; an L2 lookup is a fully divergent global load.  Strides <= 4:
+  // the first 32 false positives of a tile ride one pipelined probe batch, later ones wait
+  // for L2.  Strides 8, 16 (macro tiles): less fixed work per tile, but every false
+  // positive re-reads its bases from L2.  A seed table beyond L2 (32 B per seed) turns
+  // every probe into a DRAM access.
+  const double table = seeds > 2e6 ? 6.0 : seeds > 5e5 ? 1.6 : 1.0;
+  const double chance_cost = 140.0 * lookups_tile * chance;
+  if (D >= 8) {
+    const double per_lookup = gf ? L2_LOOKUP_CYCLES : 15.0 + 1.0 * NH;
+    return 212.0 + lookups_lane * per_lookup + 30.0 * table * hits + chance_cost;
+  }
+  const double per_hit = 4.4 * table;
   const double per_lookup = gf ? L2_LOOKUP_CYCLES : 29.0 + 2.0 * NH;
   return 136.0 + lookups_lane * per_lookup + per_hit * (hits < 32 ? hits : 32) +
-         (hits > 32 ? 2.0 * per_hit * (hits - 32) : 0.0) + 140.0 * lookups_tile * chance;
+         (hits > 32 ? 2.0 * per_hit * (hits - 32) : 0.0) + chance_cost;
 }
 
 // Resolve (s, D, NH): the caller's choice, else DKB_TUNING="s,D,NH", else the

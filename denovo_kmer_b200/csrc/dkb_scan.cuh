@@ -19,6 +19,12 @@ namespace dkb {
 
 template <int D, int NH, bool GF, bool PROF>
 struct ScanWarp {
+  // Strides 8 and 16 leave 8 / 4 lookups per lane in a 2048-position tile; SUB such tiles
+  // form a macro tile with 32 lookups per lane so that hit handling and loop overhead are
+  // paid once per macro tile.
+  static constexpr bool MACRO = D >= 8;
+  static constexpr int LPT = 64 / D;                 // lookups per lane and (sub-)tile
+  static constexpr int SUB = MACRO ? 32 / LPT : 1;   // sub-tiles per macro tile
   const ScanParams &P;
   const uint32_t *filt;
   uint16_t *hl;  // filter-hit ids of the current tile: lane << 6 | lookup index
@@ -163,6 +169,18 @@ struct ScanWarp {
     const bool act = (uint32_t)lane < n;
     const uint32_t id = act ? hl[first + lane] : (uint32_t)lane << 6;
     const int src = id >> 6;
+    if constexpr (MACRO) {
+      // macro tiles (strides 8, 16): the lookup index runs over SUB sub-tiles whose words
+      // are no longer in registers; hits are rare here, so re-read them from L2
+      const uint32_t idx = id & 63;
+      pend_p = tile_base + (idx / LPT) * WTILE + src * CHUNK + (idx % LPT) * D;
+      const uint32_t wi = pend_p >> 4;
+      pend_x = __funnelshift_r(ld_bases(wi), ld_bases(wi + 1), 2 * (pend_p & 15)) & P.seed_mask;
+      pend_b = seed_bucket(pend_x, P.st.shift);
+      if (act) pend_bucket = ldg_v4_hint(reinterpret_cast<const uint4 *>(P.st.seeds) + pend_b, keep);
+      pend_n = n;
+      return;
+    }
     const uint32_t q = (id & 63) * D;  // offset inside the owning lane's chunk
     const uint32_t c = q >> 4;
     uint32_t v[5];
@@ -237,6 +255,36 @@ struct ScanWarp {
   __device__ __forceinline__ void drain() {
     consume_pending();
     while (ct != ch) stage_c(min(ct - ch, 32u));
+  }
+
+  // ---- stage A, macro-tile form: LPT lookups of one sub-tile, hit bits in the low bits,
+  // first lookup highest.  At stride 16 every seed lies inside one word (s <= 15): no
+  // cut, no halo.
+  __device__ __forceinline__ uint32_t stage_a_sub(const uint32_t (&w)[5]) const {
+    const uint32_t mult = P.seed_mult;
+    const uint32_t fbase = (uint32_t)__cvta_generic_to_shared(filt);
+    uint32_t a = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+#pragma unroll
+      for (int t = 0; t < 16; t += D) {
+        const uint32_t x = t ? __funnelshift_r(w[c], w[c + 1], 2 * t) : w[c];
+        const uint32_t h = x * mult;
+        uint32_t word;
+        if constexpr (GF) {
+          word = ldg_u32_hint(P.bloom + __umulhi(h, P.bloom_words), keep);
+        } else {
+          const uint32_t addr = __umulhi(h, (uint32_t)BLOOM_WORDS) * P.four + fbase;
+          asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(addr));
+        }
+        uint32_t bit = word << (x & 31);
+        if (NH >= 2) bit &= word << (__umulhi(h, SEED_MULT2) & 31);
+        if (NH >= 3) bit &= word << (__umulhi(h, SEED_MULT3) & 31);
+        if (NH >= 4) bit &= word << (__umulhi(h, SEED_MULT4) & 31);
+        a = __funnelshift_l(bit, a, 1);
+      }
+    }
+    return a;
   }
 
   // ---- stage A: the shared-memory seed filter over one lane chunk ---------------
@@ -324,6 +372,71 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
   ScanWarp<D, NH, GF, PROF> W(P, filt, hl_all + warp * HL_CAP, cq_all + warp * CQ_CAP, lane);
 
   const uint32_t n_warps = gridDim.x * SCAN_WARPS;
+  if constexpr (ScanWarp<D, NH, GF, PROF>::MACRO) {
+    // Strides 8 / 16: a macro tile = SUB sub-tiles of 2048 positions (32 lookups per lane),
+    // read in groups of 4 sub-tiles (2 KB per warp per group, four LDG.128 per lane in
+    // flight), with the next group prefetched while the current one is filtered.
+    constexpr int SUB = ScanWarp<D, NH, GF, PROF>::SUB, LPT = ScanWarp<D, NH, GF, PROF>::LPT;
+    constexpr int GS = D == 16 ? 4 : 2, GPM = SUB / GS;  // sub-tiles per group, groups per macro tile
+    constexpr bool HALO = D < 16;          // at stride 16 every seed lies inside one word
+    const uint32_t n_macro = (P.n_tiles + SUB - 1) / SUB;
+    auto load_group = [&](uint32_t t0, uint4 (&v)[GS], uint32_t &edge) {
+      const uint32_t wb = t0 * WTILE_WORDS + lane * 4;
+      if ((t0 + GS) * WTILE_WORDS + 4 <= P.n_bwords) {
+#pragma unroll
+        for (int j = 0; j < GS; j++)
+          v[j] = __ldcs(reinterpret_cast<const uint4 *>(P.bases + wb + j * WTILE_WORDS));
+        edge = 0;
+        if (HALO && lane == 31) edge = __ldg(P.bases + (t0 + GS) * WTILE_WORDS);
+      } else {  // the stream ends inside this group
+#pragma unroll
+        for (int j = 0; j < GS; j++) {
+          const uint32_t q = wb + j * WTILE_WORDS;
+          v[j].x = q < P.n_bwords ? P.bases[q] : 0u;
+          v[j].y = q + 1 < P.n_bwords ? P.bases[q + 1] : 0u;
+          v[j].z = q + 2 < P.n_bwords ? P.bases[q + 2] : 0u;
+          v[j].w = q + 3 < P.n_bwords ? P.bases[q + 3] : 0u;
+        }
+        const uint32_t e = (t0 + GS) * WTILE_WORDS;
+        edge = HALO && e < P.n_bwords ? P.bases[e] : 0u;
+      }
+    };
+    uint32_t macro = blockIdx.x * SCAN_WARPS + warp;
+    int g = 0;
+    uint4 nxt[GS];
+    uint32_t nxt_edge = 0;
+    if (macro < n_macro) load_group(macro * SUB, nxt, nxt_edge);
+    uint32_t acc = 0;
+    while (macro < n_macro) {
+      uint4 v[GS];
+#pragma unroll
+      for (int j = 0; j < GS; j++) v[j] = nxt[j];
+      const uint32_t edge = nxt_edge;
+      const uint32_t cur_macro = macro;
+      const bool last_group = g == GPM - 1;
+      if (last_group) { macro += n_warps; g = 0; } else { g++; }
+      if (macro < n_macro) load_group(macro * SUB + g * GS, nxt, nxt_edge);
+#pragma unroll
+      for (int j = 0; j < GS; j++) {
+        uint32_t w[5] = {v[j].x, v[j].y, v[j].z, v[j].w, 0};
+        if constexpr (HALO) {
+          // lanes 0..30 take lane + 1's first word; lane 31 takes the first word of the
+          // next sub-tile (lane 0's, or the group's edge word)
+          const uint32_t up = __shfl_down_sync(FULL_MASK, w[0], 1);
+          const uint32_t wrap = j + 1 < GS ? __shfl_sync(FULL_MASK, v[j + 1 < GS ? j + 1 : j].x, 0)
+                                           : edge;
+          w[4] = lane == 31 ? wrap : up;
+        }
+        acc = acc << LPT | W.stage_a_sub(w);
+      }
+      if (last_group) {
+        W.consume_pending();
+        const uint32_t w0[5] = {0, 0, 0, 0, 0};
+        W.handle_hits(acc, 0, w0, cur_macro * SUB * WTILE);
+        acc = 0;
+      }
+    }
+  } else {
   uint32_t tile = blockIdx.x * SCAN_WARPS + warp;
   uint32_t nxt[5];
   if (tile < P.n_tiles) load_tile(P, tile, lane, nxt);
@@ -337,6 +450,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
     W.stage_a(w, acc0, acc1);
     W.consume_pending();  // the previous tile's seed buckets have had a whole stage A to arrive
     W.handle_hits(acc0, acc1, w, tile * WTILE);
+  }
   }
   W.drain();
 
