@@ -384,8 +384,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
       const uint32_t wb = t0 * WTILE_WORDS + lane * 4;
       if ((t0 + GS) * WTILE_WORDS + 4 <= P.n_bwords) {
 #pragma unroll
-        for (int j = 0; j < GS; j++)
-          v[j] = __ldcs(reinterpret_cast<const uint4 *>(P.bases + wb + j * WTILE_WORDS));
+        for (int j = 0; j < GS; j++)  // normal L2 priority: filter hits re-read these sectors soon
+          v[j] = __ldg(reinterpret_cast<const uint4 *>(P.bases + wb + j * WTILE_WORDS));
         edge = 0;
         if (HALO && lane == 31) edge = __ldg(P.bases + (t0 + GS) * WTILE_WORDS);
       } else {  // the stream ends inside this group
