@@ -165,8 +165,8 @@ double tile_cost(double n_entries, bool hints, int k, int s, int D, int NH, bool
   const double table = seeds > 2e6 ? 6.0 : seeds > 5e5 ? 1.6 : 1.0;
   const double chance_cost = 140.0 * lookups_tile * chance;
   if (D >= 8) {
-    const double per_lookup = gf ? L2_LOOKUP_CYCLES : 15.0 + 1.0 * NH;
-    return 212.0 + lookups_lane * per_lookup + 30.0 * table * hits + chance_cost;
+    const double per_lookup = gf ? L2_LOOKUP_CYCLES : 16.0 + 1.0 * NH;
+    return 160.0 + lookups_lane * per_lookup + 16.0 * table * hits + chance_cost;
   }
   const double per_hit = 4.4 * table;
   const double per_lookup = gf ? L2_LOOKUP_CYCLES : 29.0 + 2.0 * NH;
