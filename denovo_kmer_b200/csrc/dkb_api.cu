@@ -305,7 +305,10 @@ int launch_scan(dkb_ctx *ctx, const uint32_t *d_bases, const uint32_t *d_mask,
   if (!fn) return fail(ctx, DKB_EINVAL, "no scan kernel for this tuning");
   CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)SCAN_SMEM_BYTES));  // same carve-out in both filter modes
-  uint32_t grid = (P.n_tiles + SCAN_WARPS - 1) / SCAN_WARPS;
+  // one CTA per SM; short batches get one CTA per work unit (tile, or macro tile of 4-8
+  // tiles at strides 8/16) so that they still spread over the SMs
+  const uint32_t per_unit = ctx->D >= 8 ? 32u / (64u / ctx->D) : 1u;
+  uint32_t grid = (P.n_tiles + per_unit - 1) / per_unit;
   if (grid > (uint32_t)ctx->n_sms) grid = ctx->n_sms;
   if (grid == 0) return DKB_OK;
   if (ctx->ev_pending.size() >= 256) collect_timing(ctx);

@@ -3,7 +3,8 @@
 // src/counter.rs's membership counting; both unmounted, DESIGN.md §2 is the spec).
 //
 // Every stream position p with p % D == 0 has its s-mer tested against a
-// seed filter held in shared memory (stage A, the only per-position work).
+// seed filter held in shared memory — or, for very large candidate tables, in
+// L2 — (stage A, the only per-position work).
 // Filter hits are compacted per warp tile and verified, 32 at a time, against
 // the exact seed table in L2 (stage B, one 16-byte bucket load per hit, issued
 // one tile ahead of its use).  A verified seed carries the offsets j at which
@@ -374,8 +375,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
   const uint32_t n_warps = gridDim.x * SCAN_WARPS;
   if constexpr (ScanWarp<D, NH, GF, PROF>::MACRO) {
     // Strides 8 / 16: a macro tile = SUB sub-tiles of 2048 positions (32 lookups per lane),
-    // read in groups of 4 sub-tiles (2 KB per warp per group, four LDG.128 per lane in
-    // flight), with the next group prefetched while the current one is filtered.
+    // read in groups of GS sub-tiles (GS LDG.128 per lane in flight, 1-2 KB per warp), with
+    // the next group prefetched while the current one is filtered.
     constexpr int SUB = ScanWarp<D, NH, GF, PROF>::SUB, LPT = ScanWarp<D, NH, GF, PROF>::LPT;
     constexpr int GS = D == 16 ? 4 : 2, GPM = SUB / GS;  // sub-tiles per group, groups per macro tile
     constexpr bool HALO = D < 16;          // at stride 16 every seed lies inside one word
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
         edge = HALO && e < P.n_bwords ? P.bases[e] : 0u;
       }
     };
-    uint32_t macro = blockIdx.x * SCAN_WARPS + warp;
+    uint32_t macro = warp * gridDim.x + blockIdx.x;  // consecutive units on different SMs
     int g = 0;
     uint4 nxt[GS];
     uint32_t nxt_edge = 0;
@@ -437,7 +438,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
       }
     }
   } else {
-  uint32_t tile = blockIdx.x * SCAN_WARPS + warp;
+  uint32_t tile = warp * gridDim.x + blockIdx.x;  // consecutive tiles on different SMs
   uint32_t nxt[5];
   if (tile < P.n_tiles) load_tile(P, tile, lane, nxt);
   for (; tile < P.n_tiles; tile += n_warps) {
