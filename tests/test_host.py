@@ -206,3 +206,29 @@ int main(void) {
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
     assert "no usable CUDA device" in out.stdout
+
+
+def _build_cpp_trio(tmp_path):
+    import subprocess
+    from denovo_kmer_b200 import _lib
+    exe = tmp_path / "cpp_trio"
+    libdir = os.path.dirname(_lib.SO_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(HERE, "cpp_trio.cpp"), "-o", str(exe), "-L", libdir, "-ldkb",
+                           f"-Wl,-rpath,{libdir}"])
+    return subprocess.run([str(exe)], capture_output=True, text=True)
+
+
+def test_cpp_host_layer_builds_and_refuses_without_gpu(dkb, tmp_path):
+    """include/dkb.hpp (RAII C++ layer) compiles, the host-side pieces give the expected
+    entry and stream sizes, and without a GPU the context throws DKB_ENODEV."""
+    import torch
+    out = _build_cpp_trio(tmp_path)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert out.stdout.strip() == ("gpu-ok" if torch.cuda.is_available() else "no-gpu")
+
+
+@pytest.mark.gpu
+def test_cpp_host_layer_on_gpu(dkb, tmp_path):
+    out = _build_cpp_trio(tmp_path)
+    assert out.returncode == 0 and out.stdout.strip() == "gpu-ok", (out.returncode, out.stdout, out.stderr)
