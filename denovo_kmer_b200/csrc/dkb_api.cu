@@ -67,7 +67,7 @@ struct dkb_ctx {
   } stage[2];
   int next_stage = 0;
   uint64_t scan_launches = 0, positions_scanned = 0;
-  bool smem_attr_set = false;
+  std::vector<const void *> smem_ready;  // scan kernels whose shared-memory limit is raised
 };
 
 namespace {
@@ -303,8 +303,13 @@ int launch_scan(dkb_ctx *ctx, const uint32_t *d_bases, const uint32_t *d_mask,
   P.prof = ctx->d_prof;
   scan_fn fn = pick_scan(ctx->D, ctx->NH, ctx->gf, ctx->prof);
   if (!fn) return fail(ctx, DKB_EINVAL, "no scan kernel for this tuning");
-  CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)SCAN_SMEM_BYTES));  // same carve-out in both filter modes
+  bool ready = false;
+  for (const void *f : ctx->smem_ready) ready |= f == (const void *)fn;
+  if (!ready) {  // same carve-out in both filter modes
+    CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)SCAN_SMEM_BYTES));
+    ctx->smem_ready.push_back((const void *)fn);
+  }
   // one CTA per SM; short batches get one CTA per work unit (tile, or macro tile of 4-8
   // tiles at strides 8/16) so that they still spread over the SMs
   const uint32_t per_unit = ctx->D >= 8 ? 32u / (64u / ctx->D) : 1u;
