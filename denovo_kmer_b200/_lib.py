@@ -56,6 +56,8 @@ SYMBOLS = {
     "dkb_batch_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]),
     "dkb_batch_submit_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                           C.c_int]),
+    "dkb_batch_submit_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_size_t, C.c_int, C.c_int]),
     "dkb_sync": (C.c_int, [C.c_void_p]),
     "dkb_counts_reset": (C.c_int, [C.c_void_p]),
     "dkb_entry_counts_fetch": (C.c_int, [C.c_void_p, u32p]),

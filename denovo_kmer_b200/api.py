@@ -183,6 +183,17 @@ class KmerCounter:
         self._ck(self._L.dkb_batch_submit(self._h, stream.bases2.ctypes.data,
                                           stream.mask1.ctypes.data, stream.n_positions, sample))
 
+    def submit_reads(self, seq, qual, offsets, sample: int, min_baseq: int = DEFAULT_MIN_BASEQ,
+                     four_bit: bool = False):
+        """Decoded reads (ASCII, or BAM 4-bit codes when four_bit) packed on the GPU."""
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        qual = None if qual is None else np.ascontiguousarray(qual, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self._keep.append((seq, qual, offsets))
+        self._ck(self._L.dkb_batch_submit_reads(
+            self._h, seq.ctypes.data, int(four_bit), None if qual is None else qual.ctypes.data,
+            offsets.ctypes.data, len(offsets) - 1, min_baseq, sample))
+
     def submit_device(self, d_bases2: int, d_mask1: int, n_positions: int, sample: int):
         """Device pointers (ints) of a resident stream."""
         self._ck(self._L.dkb_batch_submit_device(self._h, d_bases2, d_mask1, n_positions, sample))

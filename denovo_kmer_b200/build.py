@@ -5,7 +5,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(_HERE, "csrc", f) for f in ("dkb_api.cu", "dkb_host.cpp")]
 DEPS = SRC + [os.path.join(_HERE, "csrc", f) for f in
-              ("dkb_device.cuh", "dkb_scan.cuh", "dkb_build.cuh")] + [
+              ("dkb_device.cuh", "dkb_scan.cuh", "dkb_build.cuh", "dkb_pack.cuh")] + [
     os.path.join(_HERE, "..", "include", "dkb.h")]
 OUT = os.path.join(_HERE, "libdkb.so")
 NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-O3", "-lineinfo",

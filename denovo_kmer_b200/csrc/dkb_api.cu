@@ -13,6 +13,7 @@
 
 #include "../../include/dkb.h"
 #include "dkb_build.cuh"
+#include "dkb_pack.cuh"
 #include "dkb_scan.cuh"
 
 using namespace dkb;
@@ -62,6 +63,10 @@ struct dkb_ctx {
   struct Stage {
     uint32_t *bases = nullptr, *mask = nullptr;
     size_t bases_cap = 0, mask_cap = 0;  // in words
+    // raw reads for the device-side packer (dkb_batch_submit_reads)
+    uint8_t *seq = nullptr, *qual = nullptr;
+    uint64_t *offsets = nullptr, *nib = nullptr;
+    size_t seq_cap = 0, qual_cap = 0, off_cap = 0, nib_cap = 0;  // bytes / elements
     cudaEvent_t copied = nullptr, freed = nullptr;
     bool in_use = false;
   } stage[2];
@@ -336,6 +341,16 @@ int launch_scan(dkb_ctx *ctx, const uint32_t *d_bases, const uint32_t *d_mask,
   return DKB_OK;
 }
 
+// Grow a staging buffer (elements of T); the caller has made sure no kernel still reads it.
+template <typename T>
+int grow(dkb_ctx *ctx, T *&p, size_t &cap, size_t need) {
+  if (cap >= need) return DKB_OK;
+  dfree(p);
+  cap = need + need / 8 + 256;
+  CU(cudaMalloc(&p, cap * sizeof(T)));
+  return DKB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -409,6 +424,10 @@ int dkb_ctx_destroy(dkb_ctx *ctx) {
   for (auto &st : ctx->stage) {
     dfree(st.bases);
     dfree(st.mask);
+    dfree(st.seq);
+    dfree(st.qual);
+    dfree(st.offsets);
+    dfree(st.nib);
     if (st.copied) cudaEventDestroy(st.copied);
     if (st.freed) cudaEventDestroy(st.freed);
   }
@@ -595,6 +614,78 @@ int dkb_batch_submit(dkb_ctx *ctx, const uint32_t *bases2, const uint32_t *mask1
   CU(cudaEventRecord(st.copied, ctx->s_copy));
   CU(cudaStreamWaitEvent(ctx->s_scan, st.copied, 0));
   int rc = launch_scan(ctx, st.bases, st.mask, n_positions, sample);
+  if (rc != DKB_OK) return rc;
+  CU(cudaEventRecord(st.freed, ctx->s_scan));
+  st.in_use = true;
+  return DKB_OK;
+}
+
+int dkb_batch_submit_reads(dkb_ctx *ctx, const uint8_t *seq, int seq_format, const uint8_t *qual,
+                           const uint64_t *offsets, size_t n_reads, int min_baseq, int sample) {
+  if (!ctx) return fail(nullptr, DKB_EINVAL, "ctx is null");
+  if (!ctx->d_tslots) return fail(ctx, DKB_ESTATE, "dkb_table_build must come first");
+  if (sample < 0 || sample >= DKB_N_SAMPLES) return fail(ctx, DKB_EINVAL, "sample must be 0, 1 or 2");
+  if (seq_format != 0 && seq_format != 1) return fail(ctx, DKB_EINVAL, "seq_format must be 0 (ASCII) or 1 (BAM 4-bit)");
+  if (n_reads == 0) return DKB_OK;
+  if (!seq || !offsets) return fail(ctx, DKB_EINVAL, "null read buffer");
+  if (n_reads >= 0xFFFFFFFFull) return fail(ctx, DKB_EINVAL, "too many reads in one batch");
+  for (size_t r = 0; r < n_reads; r++)
+    if (offsets[r + 1] < offsets[r]) return fail(ctx, DKB_EINVAL, "offsets must not decrease");
+  const uint64_t n_pos = dkb_stream_positions(offsets, n_reads);
+  if (n_pos > 0xFFFFF000ull) return fail(ctx, DKB_EINVAL, "batch too long (max 2^32 - 4096 positions)");
+  const uint64_t n_bases = offsets[n_reads] - offsets[0];
+  CU(cudaSetDevice(ctx->device));
+  const size_t bw = dkb_stream_bases_words(n_pos), mw = dkb_stream_mask_words(n_pos);
+  // BAM keeps every read's 4-bit codes byte-aligned: (len + 1) / 2 bytes per read
+  std::vector<uint64_t> nib;
+  uint64_t seq_bytes = n_bases;
+  if (seq_format == 1) {
+    nib.resize(n_reads);
+    uint64_t b = 0;
+    for (size_t r = 0; r < n_reads; r++) {
+      nib[r] = b;
+      b += (offsets[r + 1] - offsets[r] + 1) / 2;
+    }
+    seq_bytes = b;
+  }
+  dkb_ctx::Stage &st = ctx->stage[ctx->next_stage];
+  ctx->next_stage ^= 1;
+  if (st.in_use) CU(cudaEventSynchronize(st.freed));  // buffers may be regrown below
+  int rc;
+  if ((rc = grow(ctx, st.bases, st.bases_cap, bw)) != DKB_OK) return rc;
+  if ((rc = grow(ctx, st.mask, st.mask_cap, mw)) != DKB_OK) return rc;
+  if ((rc = grow(ctx, st.seq, st.seq_cap, (size_t)seq_bytes)) != DKB_OK) return rc;
+  if (qual && (rc = grow(ctx, st.qual, st.qual_cap, (size_t)n_bases)) != DKB_OK) return rc;
+  if ((rc = grow(ctx, st.offsets, st.off_cap, n_reads + 1)) != DKB_OK) return rc;
+  if (seq_format == 1 && (rc = grow(ctx, st.nib, st.nib_cap, n_reads)) != DKB_OK) return rc;
+  // the reads of this batch start at offsets[0] in the caller's arrays; device copies start at 0
+  const uint8_t *seq0 = seq_format == 1 ? seq : seq + offsets[0];
+  CU(cudaMemcpyAsync(st.seq, seq0, seq_bytes, cudaMemcpyHostToDevice, ctx->s_copy));
+  if (qual) CU(cudaMemcpyAsync(st.qual, qual + offsets[0], n_bases, cudaMemcpyHostToDevice, ctx->s_copy));
+  CU(cudaMemcpyAsync(st.offsets, offsets, (n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->s_copy));
+  if (seq_format == 1) {
+    CU(cudaMemcpyAsync(st.nib, nib.data(), n_reads * 8, cudaMemcpyHostToDevice, ctx->s_copy));
+    CU(cudaStreamSynchronize(ctx->s_copy));  // nib is a local vector
+  }
+  CU(cudaEventRecord(st.copied, ctx->s_copy));
+  CU(cudaStreamWaitEvent(ctx->s_scan, st.copied, 0));
+  PackParams Q;
+  Q.seq = st.seq;
+  Q.qual = qual ? st.qual : nullptr;
+  Q.offsets = st.offsets;
+  Q.nib_start = st.nib;
+  Q.n_reads = (uint32_t)n_reads;
+  Q.n_pos = n_pos;
+  Q.n_bwords = (uint32_t)bw;
+  Q.n_mwords = (uint32_t)mw;
+  Q.min_baseq = min_baseq;
+  Q.four_bit = seq_format;
+  Q.bases2 = st.bases;
+  Q.mask1 = st.mask;
+  const int TB = 256;
+  k_pack<<<(uint32_t)((mw + TB - 1) / TB), TB, 0, ctx->s_scan>>>(Q);
+  CU(cudaGetLastError());
+  rc = launch_scan(ctx, st.bases, st.mask, n_pos, sample);
   if (rc != DKB_OK) return rc;
   CU(cudaEventRecord(st.freed, ctx->s_scan));
   st.in_use = true;

@@ -1,0 +1,78 @@
+// dkb_pack.cuh — kernel 0: device-side read packer (widening row f1 of DESIGN.md §0).
+// Same output as the host packer dkb_pack_reads, bit for bit, from decoded reads left in
+// the form the BAM layer already holds: bases as ASCII or as BAM's 4-bit codes, one
+// quality byte per base.  One thread builds 32 stream positions (two base words, one
+// mask word), so no output word is shared between threads.
+#pragma once
+#include "dkb_device.cuh"
+
+namespace dkb {
+
+struct PackParams {
+  const uint8_t *seq;        // ASCII bases, or 4-bit codes (high nibble first, BAM order)
+  const uint8_t *qual;       // may be null
+  const uint64_t *offsets;   // [n_reads + 1] base offsets of the reads in seq/qual (ASCII form)
+  const uint64_t *nib_start; // [n_reads] byte offset of each read's first nibble pair (4-bit form)
+  uint32_t n_reads;
+  uint64_t n_pos;
+  uint32_t n_bwords, n_mwords;  // output sizes (dkb_stream_*_words)
+  int min_baseq;
+  int four_bit;
+  uint32_t *bases2;
+  uint32_t *mask1;
+};
+
+// BAM 4-bit code -> 2-bit code (A=1 C=2 G=4 T=8), 4 = not a plain base
+__device__ __forceinline__ uint32_t nib_to_code(uint32_t n) {
+  return n == 1 ? 0u : n == 2 ? 1u : n == 4 ? 2u : n == 8 ? 3u : 4u;
+}
+__device__ __forceinline__ uint32_t ascii_to_code(uint32_t c) {
+  c &= 0xDFu;  // fold case
+  return c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
+}
+
+__global__ void k_pack(const PackParams Q) {
+  const uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // mask word index
+  const uint64_t p0 = m * 32;
+  if (m >= Q.n_mwords) return;
+  uint32_t b0 = 0, b1 = 0, mk = 0;
+  if (p0 < Q.n_pos && Q.n_reads) {
+    // read r starts at stream position offsets[r] - offsets[0] + r; find the last start <= p0
+    const uint64_t o0 = Q.offsets[0];
+    uint32_t lo = 0, hi = Q.n_reads;
+    while (hi - lo > 1) {
+      const uint32_t mid = lo + (hi - lo) / 2;
+      if (Q.offsets[mid] - o0 + mid <= p0) lo = mid; else hi = mid;
+    }
+    uint32_t r = lo;
+    uint64_t start = Q.offsets[r] - o0 + r;
+    uint64_t len = Q.offsets[r + 1] - Q.offsets[r];
+    uint64_t i = p0 - start;  // offset inside read r; i == len is the separator
+    for (uint32_t t = 0; t < 32 && p0 + t < Q.n_pos; t++) {
+      if (i < len) {
+        uint32_t c;
+        if (Q.four_bit) {
+          const uint32_t byte = Q.seq[Q.nib_start[r] + (i >> 1)];
+          c = nib_to_code((i & 1) ? (byte & 15u) : (byte >> 4));
+        } else {
+          c = ascii_to_code(Q.seq[Q.offsets[r] - o0 + i]);  // device copies start at the batch's first base
+        }
+        const bool ok = c < 4 && (Q.qual == nullptr || (int)Q.qual[Q.offsets[r] - o0 + i] >= Q.min_baseq);
+        if (ok) {
+          mk |= 1u << t;
+          if (t < 16) b0 |= c << (2 * t); else b1 |= c << (2 * (t - 16));
+        }
+        i++;
+      } else {  // separator, then the next read
+        r++;
+        i = 0;
+        if (r < Q.n_reads) len = Q.offsets[r + 1] - Q.offsets[r]; else len = 0;
+      }
+    }
+  }
+  if (2 * m < Q.n_bwords) Q.bases2[2 * m] = b0;
+  if (2 * m + 1 < Q.n_bwords) Q.bases2[2 * m + 1] = b1;
+  Q.mask1[m] = mk;
+}
+
+}  // namespace dkb

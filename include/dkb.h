@@ -150,6 +150,13 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
  * valid until dkb_sync. */
 int dkb_batch_submit(dkb_ctx *ctx, const uint32_t *bases2, const uint32_t *mask1,
                      uint64_t n_positions, int sample);
+/* Decoded reads as the BAM layer holds them: the packing (what dkb_pack_reads does on the
+ * host) runs on the GPU.  seq_format 0: ASCII bases, read r at seq[offsets[r]..offsets[r+1]);
+ * 1: BAM 4-bit codes (=ACMGRSVTWYHKDBN, high nibble first), every read starting on a byte
+ * boundary with (len + 1) / 2 bytes, reads back to back from seq[0].  qual (may be NULL):
+ * one byte per base at qual[offsets[r]..].  Same stream, bit for bit, as dkb_pack_reads. */
+int dkb_batch_submit_reads(dkb_ctx *ctx, const uint8_t *seq, int seq_format, const uint8_t *qual,
+                           const uint64_t *offsets, size_t n_reads, int min_baseq, int sample);
 /* Device-resident buffers (16-byte aligned, dkb_stream_*_words long). */
 int dkb_batch_submit_device(dkb_ctx *ctx, const uint32_t *d_bases2, const uint32_t *d_mask1,
                             uint64_t n_positions, int sample);

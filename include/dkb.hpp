@@ -106,6 +106,15 @@ class Counter {
   void submit(const Stream &s, int sample) {
     check(dkb_batch_submit(ctx_, s.bases2.data(), s.mask1.data(), s.n_positions, sample), ctx_);
   }
+  // decoded reads packed on the GPU (ASCII bases, or BAM 4-bit codes when four_bit)
+  void submit_reads(const std::vector<uint8_t> &seq, const std::vector<uint8_t> &qual,
+                    const std::vector<uint64_t> &offsets, int min_baseq, int sample,
+                    bool four_bit = false) {
+    check(dkb_batch_submit_reads(ctx_, seq.data(), four_bit ? 1 : 0, qual.empty() ? nullptr : qual.data(),
+                                 offsets.data(), offsets.empty() ? 0 : offsets.size() - 1, min_baseq,
+                                 sample),
+          ctx_);
+  }
   void sync() { check(dkb_sync(ctx_), ctx_); }
   void reset_counts() { check(dkb_counts_reset(ctx_), ctx_); }
   std::vector<uint32_t> entry_counts() {  // [3 samples][n_entries]

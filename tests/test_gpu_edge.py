@@ -196,3 +196,54 @@ def test_context_lifecycle(dkb, orc):
         assert k1.tuning()[:3] == (15, 2, 2)
         st = k1.stats()
         assert st["n_entries"] == len(ent_b31) and st["scan_launches"] == 3
+
+
+def _to_bam4(seq, off):
+    """ASCII reads -> BAM 4-bit codes, every read byte-aligned (what htslib keeps in memory)."""
+    code = np.full(256, 15, np.uint8)  # N
+    for ch, v in zip(b"=ACMGRSVTWYHKDBN", range(16)):
+        code[ch] = v
+        code[ord(chr(ch).lower())] = v
+    out = []
+    for a, b in zip(off[:-1], off[1:]):
+        c = code[seq[int(a):int(b)]]
+        if len(c) % 2:
+            c = np.concatenate([c, np.zeros(1, np.uint8)])
+        out.append((c[0::2] << 4) | c[1::2])
+    return np.concatenate(out) if out else np.zeros(0, np.uint8)
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_device_packer_matches_host_packer(dkb, orc, ragged):
+    """dkb_batch_submit_reads (packing on the GPU from ASCII or BAM 4-bit reads) must give
+    the counts of the host-packed path and of the oracle."""
+    k = 21
+    trio = synth.make_trio_host(60_000, 12, 10, k, seed=61, ragged=ragged, n_rate=0.01,
+                                lowq_frac=0.1, indel_frac=0.3)
+    ent = dkb.variant_kmers(trio.variant_tuples(), k)
+    ks = orc.KmerSet(ent.keys, ent.variant, ent.allele)
+    want = np.zeros((3, len(ent)), dtype=np.uint64)
+    for smp in range(3):
+        ks.count_reads(*trio.reads[smp], k, 20, counts=want[smp])
+    for four_bit in (False, True):
+        with dkb.KmerCounter(k) as kc:
+            kc.build_table(ent)
+            for smp in range(3):
+                seq, qual, off = trio.reads[smp]
+                n = len(off) - 1
+                cuts = [0, n // 3, n // 3 + 1, n]  # three batches, the middle one a single read
+                for a, b in zip(cuts[:-1], cuts[1:]):
+                    o = off[a:b + 1]
+                    if four_bit:
+                        kc.submit_reads(_to_bam4(seq, o), qual, o, smp, 20, four_bit=True)
+                    else:
+                        kc.submit_reads(seq, qual, o, smp, 20)
+            got = kc.entry_counts()
+        assert np.array_equal(got.astype(np.uint64), want), four_bit
+    # no qualities, min_baseq irrelevant
+    with dkb.KmerCounter(k) as kc:
+        kc.build_table(ent)
+        seq, qual, off = trio.reads[0]
+        kc.submit_reads(seq, None, off, 0, 99)
+        got = kc.entry_counts()[0]
+    assert np.array_equal(got.astype(np.uint64), ks.count_reads(seq, None, off, k, 0))
