@@ -483,7 +483,9 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
   ctx->n_entries = n;
   ctx->n_variants = n_variants;
   const size_t n1 = n ? n : 1, nv1 = n_variants ? n_variants : 1;
-  ctx->table_slots = pow2_at_least(8 * (uint64_t)n + 2);  // <= 0.25 entries per 2-slot bucket
+  int slots_per_entry = 8;
+  if (const char *e = getenv("DKB_KEY_SLOTS_PER_ENTRY")) slots_per_entry = atoi(e) > 0 ? atoi(e) : 8;
+  ctx->table_slots = pow2_at_least((uint64_t)slots_per_entry * n + 2);  // <= 0.25 entries per 2-slot bucket
   uint16_t *d_wi = nullptr, *d_wc = nullptr;
   uint32_t *d_slot_of = nullptr;
   uint32_t *d_set = nullptr;
