@@ -91,3 +91,42 @@ def test_split_additivity_and_tuning_invariance(dkb):
     assert base.sum() > 100_000
     for t, r in results.items():
         assert np.array_equal(r, base), t
+
+
+@pytest.mark.parametrize("tuning", [None, (14, 4, 2, 1), (15, 16, 2, 1), (15, 8, 2, 2)])
+def test_maximum_batch_length(dkb, orc, tuning):
+    """One batch of the maximum length (2^32 - 4096 positions, 1.07 GB of packed bases):
+    random sequence with a real trio's reads packed into its last positions.  Every 32-bit
+    position computation near the top of the range must hold: counts equal the oracle's on
+    the real reads (a random 31-mer matching the table by chance has probability ~1e-9)."""
+    dev = torch.device("cuda:0")
+    trio = synth.make_trio_host(50_000, 10, 10, K, seed=91)
+    entries = dkb.variant_kmers(trio.variant_tuples(), K)
+    seq, qual, off = trio.reads[0]
+    tail = dkb.pack_reads(seq, qual, off, 20)
+    n_max = (1 << 32) - 4096
+    n_head = (n_max - tail.n_positions) // 128 * 128
+    n_pos = n_head + tail.n_positions
+    bw, mw = dkb.stream_words(n_pos)
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    b2 = torch.empty(bw, dtype=torch.int32, device=dev)
+    for a in range(0, n_head // 16, 1 << 26):
+        e = min(a + (1 << 26), n_head // 16)
+        b2[a:e] = torch.randint(-2 ** 31, 2 ** 31 - 1, (e - a,), dtype=torch.int32, device=dev, generator=g)
+    m1 = torch.full((mw,), -1, dtype=torch.int32, device=dev)
+    tb = torch.from_numpy(tail.bases2.view(np.int32)).to(dev)
+    tm = torch.from_numpy(tail.mask1.view(np.int32)).to(dev)
+    b2[n_head // 16: n_head // 16 + tb.numel()] = tb[: bw - n_head // 16]
+    m1[n_head // 32: n_head // 32 + tm.numel()] = tm[: mw - n_head // 32]
+    torch.cuda.synchronize()
+    ks = orc.KmerSet(entries.keys, entries.variant, entries.allele)
+    want = ks.count_reads(seq, qual, off, K, 20)
+    with dkb.KmerCounter(K, tuning=tuning) as kc:
+        kc.build_table(entries)
+        kc.submit_device(b2.data_ptr(), m1.data_ptr(), n_pos, 0)
+        got = kc.entry_counts()[0]
+        with pytest.raises(dkb.DkbError):  # one position more than the limit
+            kc.submit_device(b2.data_ptr(), m1.data_ptr(), n_max + 1, 0)
+    assert np.array_equal(got.astype(np.uint64), want), tuning
+    assert want.sum() > 0
