@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libdkb.so")
+SO_PATH = os.environ.get("DKB_LIBRARY") or os.path.join(_HERE, "libdkb.so")  # override: A/B builds
 
 OK, EINVAL, ECUDA, ENOMEM, ESTATE, ENODEV = range(6)
 
