@@ -224,6 +224,33 @@ struct ScanWarp {
       excl = incl - cnt;
     }
     const uint32_t tag = (uint32_t)lane << 6;
+    if constexpr (!MACRO) {
+      if (total <= (uint32_t)HL_CAP) {
+        // common case: the whole tile fits the id list, no bounds checks
+        uint32_t idx = excl;
+        uint32_t a = acc0;
+        while (a) {
+          const int i = __clz(a);
+          a ^= 0x80000000u >> i;
+          hl[idx++] = (uint16_t)(tag + i);
+        }
+        if (D == 1) {
+          a = acc1;
+          while (a) {
+            const int i = __clz(a);
+            a ^= 0x80000000u >> i;
+            hl[idx++] = (uint16_t)(tag + 32 + i);
+          }
+        }
+        __syncwarp();
+        for (uint32_t r = 0; r < total; r += 32) {
+          consume_pending();  // at most one batch of probes in flight
+          issue_probes(r, min(total - r, 32u), w, tile_base);
+        }
+        __syncwarp();
+        return;
+      }
+    }
     // the id list holds HL_CAP hits; denser tiles (low-complexity sequence) take more passes
     for (uint32_t base = 0; base < total; base += HL_CAP) {
       uint32_t idx = excl - base;  // wraps below zero for hits of earlier passes
