@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
     // read in groups of GS sub-tiles (GS LDG.128 per lane in flight, 1-2 KB per warp), with
     // the next group prefetched while the current one is filtered.
     constexpr int SUB = ScanWarp<D, NH, GF, PROF>::SUB, LPT = ScanWarp<D, NH, GF, PROF>::LPT;
-    constexpr int GS = D == 16 ? 4 : 2, GPM = SUB / GS;  // sub-tiles per group, groups per macro tile
+    constexpr int GS = 2, GPM = SUB / GS;  // sub-tiles per group, groups per macro tile
     constexpr bool HALO = D < 16;          // at stride 16 every seed lies inside one word
     const uint32_t n_macro = (P.n_tiles + SUB - 1) / SUB;
     auto load_group = [&](uint32_t t0, uint4 (&v)[GS], uint32_t &edge) {
