@@ -255,8 +255,8 @@ SeedTable seed_table(const dkb_ctx *ctx) {
   SeedTable T;
   T.seeds = ctx->d_seeds;
   T.sinfo = ctx->d_sinfo;
-  T.bucket_mask = ctx->seed_slots / BUCKET - 1;
-  T.shift = 32 - log2_u32(ctx->seed_slots / BUCKET);
+  T.slot_mask = ctx->seed_slots - 1;
+  T.shift = 32 - log2_u32(ctx->seed_slots);
   return T;
 }
 
@@ -270,6 +270,11 @@ KeyTable key_table(const dkb_ctx *ctx) {
 typedef void (*scan_fn)(const ScanParams);
 
 scan_fn pick_scan(int D, int NH, bool gf, bool prof) {
+#ifdef DKB_AB_BUILD  // quick experimental builds (scripts/ab_build.sh): stride 4, 2 filter bits only
+  if (!gf && D == 4 && NH == 2)
+    return prof ? (scan_fn)k_scan<4, 2, false, true> : (scan_fn)k_scan<4, 2, false, false>;
+  return nullptr;
+#else
 #define PICKG(d, h)                                                                     \
   if (gf && D == d && NH == h)                                                          \
     return prof ? (scan_fn)k_scan<d, h, true, true> : (scan_fn)k_scan<d, h, true, false>;
@@ -284,6 +289,7 @@ scan_fn pick_scan(int D, int NH, bool gf, bool prof) {
   PICK(16, 1) PICK(16, 2) PICK(16, 3) PICK(16, 4)
 #undef PICK
   return nullptr;
+#endif
 }
 
 int launch_scan(dkb_ctx *ctx, const uint32_t *d_bases, const uint32_t *d_mask,
@@ -302,6 +308,8 @@ int launch_scan(dkb_ctx *ctx, const uint32_t *d_bases, const uint32_t *d_mask,
   P.seed_mult = SEED_MULT << (32 - 2 * ctx->s);
   P.seed_mask = (1u << (2 * ctx->s)) - 1;
   P.four = 4;
+  for (int i = 0; i < 32; i++) P.pw[i] = 1u << i;
+  P.filter_words = BLOOM_WORDS;
   P.counts = ctx->d_counts + (size_t)sample * ctx->n_entries;
   P.k = ctx->k;
   P.s = ctx->s;
@@ -544,11 +552,17 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
     CU(cudaMemcpyAsync(&n_seeds, d_nseeds, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     ctx->n_seeds = n_seeds;
-    // <= 0.5 seeds per 4-slot bucket on average: a full bucket (second load) is a 1-in-600 event
-    ctx->seed_slots = pow2_at_least(8 * (uint64_t)n_seeds + 2);
+    // At most 1/16 full (1/8 for large seed sets, which must still fit L2): a filter false
+    // positive lands on a slot marked ST_MOVED_BIT (second load) once in several hundred probes.
+    // At most 1/8 full: a filter false positive lands on a slot marked ST_MOVED_BIT (second
+    // load) about once in a hundred probes; 16 slots per seed halve that but cost more L2
+    // (measured 2-7 % slower at every stride).
+    int per_seed = 8;
+    if (const char *e = getenv("DKB_SEED_SLOTS_PER_SEED")) per_seed = atoi(e) > 1 ? atoi(e) : per_seed;
+    ctx->seed_slots = pow2_at_least((uint64_t)per_seed * n_seeds + 2);
     CU(cudaMalloc(&ctx->d_seeds, (size_t)ctx->seed_slots * 4));
     CU(cudaMalloc(&ctx->d_sinfo, (size_t)ctx->seed_slots * 4));
-    CU(cudaMemsetAsync(ctx->d_seeds, 0xFF, (size_t)ctx->seed_slots * 4, st));
+    CU(cudaMemsetAsync(ctx->d_seeds, 0x40, (size_t)ctx->seed_slots * 4, st));  // ST_EMPTY
     CU(cudaMemsetAsync(ctx->d_sinfo, 0, (size_t)ctx->seed_slots * 4, st));
     ctx->bloom_words = ctx->gf ? l2_filter_words((double)n_seeds) / 4 * 4 : (uint32_t)BLOOM_WORDS;
     CU(cudaMalloc(&ctx->d_bloom, (size_t)ctx->bloom_words * 4));

@@ -75,20 +75,24 @@ __global__ void k_apply_dead(const BuildParams B) {
   if (B.dead[i]) B.kt.slots[B.slot_of[i]].z = ENTRY_DEAD;
 }
 
-// Insert (seed, offset bit) into the bucketised seed table.
+// Insert (seed, offset bit) into the seed table: the home slot, else the first free slot
+// after it, with the home slot marked ST_MOVED_BIT so that lookups know to walk on.
 __device__ __forceinline__ void seedtab_insert(const SeedTable &T, uint32_t seed, uint32_t info) {
-  uint32_t b = seed_bucket(seed, T.shift);
+  uint32_t slot = seed_home(seed, T.shift);
+  bool home = true;
   while (true) {
-    for (int j = 0; j < BUCKET; j++) {
-      const uint32_t slot = b * BUCKET + j;
-      uint32_t old = T.seeds[slot];
-      if (old == SEED_EMPTY) old = atomicCAS(T.seeds + slot, SEED_EMPTY, seed);
-      if (old == SEED_EMPTY || old == seed) {
-        atomicOr(T.sinfo + slot, info);
-        return;
-      }
+    uint32_t old = T.seeds[slot];
+    if (old & ST_FREE_BIT) {
+      old = atomicCAS(T.seeds + slot, ST_EMPTY, seed);
+      if (old == ST_EMPTY) old = seed;
     }
-    b = (b + 1) & T.bucket_mask;
+    if ((old & ST_SEED_BITS) == seed) {
+      atomicOr(T.sinfo + slot, info);
+      return;
+    }
+    if (home) atomicOr(T.seeds + slot, ST_MOVED_BIT);  // taken by another seed
+    home = false;
+    slot = (slot + 1) & T.slot_mask;
   }
 }
 
@@ -170,7 +174,7 @@ __global__ void k_assign_seeds(const BuildParams B, bool count_only, uint32_t *s
       offs |= (uint32_t)(j / D) << (W * (ori * D + c));
       seedtab_insert(T, seed, 1u << j);
       const uint32_t h = seed * seed_mult;
-      atomicOr(bloom + __umulhi(h, bloom_words), bloom_bits(seed, h, n_hashes));
+      atomicOr(bloom + bloom_word(h, bloom_words), bloom_bits(seed, h, bloom_words, n_hashes));
     }
   }
   if (!count_only) atomicOr(&B.kt.slots[B.slot_of[i]].w, offs);

@@ -22,14 +22,17 @@ constexpr size_t SCAN_SMEM_BYTES =
 
 constexpr int MAX_SEED_LEN = 15;             // 30 bits: leaves SEED_EMPTY outside the seed space
 constexpr uint32_t SEED_MULT = 0x9E3779B1u;  // odd multiplier of the filter hash
-constexpr uint32_t SEED_MULT2 = 0x85EBCA77u; // filter bit n: bits 32..36 of hash * SEED_MULTn
-constexpr uint32_t SEED_MULT3 = 0xC2B2AE3Du;
-constexpr uint32_t SEED_MULT4 = 0x27D4EB2Fu;
 constexpr uint32_t SEEDTAB_MULT = 0xC2B2AE3Du; // seed bucket = (seed * SEEDTAB_MULT) >> shift
-constexpr uint32_t SEED_EMPTY = 0xFFFFFFFFu;
+constexpr uint32_t SEED_EMPTY = 0xFFFFFFFFu;  // free slot of the sizing set (k_assign_seeds, count_only)
+// Seed-table slot word: bits 0..29 the seed, bit 30 = slot is free, bit 31 = some seed
+// whose home is this slot lives further along (a miss must walk on).  A free slot is the
+// memset pattern 0x40.
+constexpr uint32_t ST_EMPTY = 0x40404040u;
+constexpr uint32_t ST_FREE_BIT = 0x40000000u;
+constexpr uint32_t ST_MOVED_BIT = 0x80000000u;
+constexpr uint32_t ST_SEED_BITS = 0x7FFFFFFFu;  // (word & ST_SEED_BITS) == seed  <=>  the slot holds it
 constexpr uint64_t KEY_EMPTY = ~0ull;        // keys use at most 62 bits
 constexpr uint32_t ENTRY_DEAD = 0xFFFFFFFFu; // repeated (key, owner) triple
-constexpr int BUCKET = 4;                    // seeds per seed-table bucket (16 B)
 constexpr int KBUCKET = 2;                   // slots per key-table bucket (32 B, one L2 sector)
 
 // ---- hashes ----------------------------------------------------------------
@@ -41,24 +44,27 @@ __host__ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
   return x;
 }
 
-// bucket of a seed in the exact seed table (multiplicative hash, top bits)
-__host__ __device__ __forceinline__ uint32_t seed_bucket(uint32_t seed, uint32_t shift) {
+// home slot of a seed in the exact seed table (multiplicative hash, top bits)
+__host__ __device__ __forceinline__ uint32_t seed_home(uint32_t seed, uint32_t shift) {
   return (seed * SEEDTAB_MULT) >> shift;
 }
 
-// the two filter bits of a seed whose filter hash is h (bit 31 = index 0)
-__host__ __device__ __forceinline__ uint32_t bloom_bit1(uint32_t seed) {
-  return 0x80000000u >> (seed & 31);
+// Seed filter: a blocked Bloom filter, all bits of a seed inside one 32-bit word.  With
+// h = seed * seed_mult and the 64-bit product h * n_words: the word is the product's high
+// half, bit 1 is (seed & 31), bits 2..4 are 5-bit fields taken from the top of the
+// product's LOW half - so one IMAD.WIDE yields the word and every hashed bit index.  (A
+// multiply-high per index costs 5 issue cycles per warp on sm_100 and stalls the ALU pipe
+// meanwhile, against 2.4 for IMAD.WIDE: scripts/micro/int_pipes.cu.)
+__host__ __device__ __forceinline__ uint32_t bloom_word(uint32_t h, uint32_t n_words) {
+  return (uint32_t)(((uint64_t)h * n_words) >> 32);
 }
-__host__ __device__ __forceinline__ uint32_t bloom_bitn(uint32_t h, uint32_t mult) {
-  return 0x80000000u >> ((uint32_t)(((uint64_t)h * mult) >> 32) & 31);
-}
-// all filter bits of a seed (n_hashes in 1..4)
-__host__ __device__ __forceinline__ uint32_t bloom_bits(uint32_t seed, uint32_t h, int n_hashes) {
-  uint32_t bits = bloom_bit1(seed);
-  if (n_hashes >= 2) bits |= bloom_bitn(h, SEED_MULT2);
-  if (n_hashes >= 3) bits |= bloom_bitn(h, SEED_MULT3);
-  if (n_hashes >= 4) bits |= bloom_bitn(h, SEED_MULT4);
+__host__ __device__ __forceinline__ uint32_t bloom_bits(uint32_t seed, uint32_t h, uint32_t n_words,
+                                                        int n_hashes) {
+  const uint32_t lo = (uint32_t)((uint64_t)h * n_words);
+  uint32_t bits = 1u << (seed & 31);
+  if (n_hashes >= 2) bits |= 1u << (lo >> 27);
+  if (n_hashes >= 3) bits |= 1u << ((lo >> 22) & 31);
+  if (n_hashes >= 4) bits |= 1u << ((lo >> 17) & 31);
   return bits;
 }
 
@@ -105,14 +111,15 @@ __device__ __forceinline__ uint64_t ldg_u64_hint(const void *ptr, uint64_t pol) 
 }
 
 // ---- the two lookup structures (both in L2) -----------------------------------
-// Seed table: buckets of 4 uint32 seeds (16 B, one LDG.128); sinfo[slot] = bitmap
-// of the offsets j at which some key designates this seed.  A seed lives in
-// its home bucket or, when that is full, in the next one (linear in buckets).
+// Seed table: one uint32 word per slot (see ST_*), open addressing, linear probing, at
+// most 1/8 full; sinfo[slot] = bitmap of the offsets j at which some key designates this
+// seed.  A lookup is ONE 4-byte load unless the home slot carries ST_MOVED_BIT (about one
+// slot in 400): a seed absent from an unmarked home slot is absent from the table.
 struct SeedTable {
   uint32_t *seeds;
   uint32_t *sinfo;
-  uint32_t bucket_mask;  // n_buckets - 1
-  uint32_t shift;        // 32 - log2(n_buckets)
+  uint32_t slot_mask;  // n_slots - 1
+  uint32_t shift;      // 32 - log2(n_slots)
 };
 // Key table: 16-byte slots {key lo, key hi, entry index, packed designated
 // offsets}, buckets of 2 slots = one 32-byte L2 sector (two LDG.128), a
@@ -153,6 +160,8 @@ struct ScanParams {
   uint32_t seed_mult;  // SEED_MULT << (32 - 2s): the product ignores bases beyond s
   uint32_t seed_mask;  // low 2s bits
   uint32_t four;       // = 4, opaque to the compiler: keeps the filter address on the FMA pipe
+  uint32_t pw[32];     // pw[n] = 2^n, opaque too: multiplies by these stay on the FMA pipe
+  uint32_t filter_words;  // = BLOOM_WORDS (shared-memory mode), as a run-time operand of the wide multiply
   uint32_t *counts;    // this sample's [n_entries] counters
   int k, s;
   unsigned long long *prof;  // 4 counters or nullptr

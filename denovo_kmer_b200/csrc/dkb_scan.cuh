@@ -16,6 +16,10 @@
 #pragma once
 #include "dkb_device.cuh"
 
+#ifndef DKB_X
+#define DKB_X 0  // timing experiments only (scripts/ab_build.sh): 1 = rounds without their load, 2 = no rounds
+#endif
+
 namespace dkb {
 
 template <int D, int NH, bool GF, bool PROF>
@@ -26,6 +30,7 @@ struct ScanWarp {
   static constexpr bool MACRO = D >= 8;
   static constexpr int LPT = 64 / D;                 // lookups per lane and (sub-)tile
   static constexpr int SUB = MACRO ? 32 / LPT : 1;   // sub-tiles per macro tile
+  static constexpr bool LOCAL = D == 2 || D == 4;    // lane-local hit verification
   const ScanParams &P;
   const uint32_t *filt;
   uint16_t *hl;  // filter-hit ids of the current tile: lane << 6 | lookup index
@@ -34,14 +39,14 @@ struct ScanWarp {
   int lane;
   uint32_t lt_mask;
   uint64_t keep = l2_policy_evict_last();  // cache policy of every table load
+  const uint32_t zero;                     // 0, but not to the compiler
   // stage B probes in flight (issued at the end of one tile, consumed in the next)
-  uint32_t pend_n = 0, pend_x = 0, pend_p = 0, pend_b = 0;
-  uint4 pend_bucket = {0, 0, 0, 0};
+  uint32_t pend_n = 0, pend_x = 0, pend_p = 0, pend_b = 0, pend_v = 0;
   unsigned long long n_bloom = 0, n_seed = 0, n_probe = 0, n_hit = 0;
 
   __device__ __forceinline__ ScanWarp(const ScanParams &p, const uint32_t *f, uint16_t *h,
                                       uint64_t *c, int l)
-      : P(p), filt(f), hl(h), cq(c), lane(l), lt_mask((1u << l) - 1) {}
+      : P(p), filt(f), hl(h), cq(c), lane(l), lt_mask((1u << l) - 1), zero(p.four >> 3) {}
 
   __device__ __forceinline__ uint32_t ld_bases(uint32_t wi) const {
     return wi < P.n_bwords ? __ldg(P.bases + wi) : 0u;
@@ -116,60 +121,169 @@ struct ScanWarp {
     __syncwarp();
   }
 
-  // ---- stage B, second half: use the seed buckets loaded one tile ago -----------
-  __device__ __forceinline__ void consume_pending() {
-    if (pend_n == 0) return;
-    const bool act = (uint32_t)lane < pend_n;
-    const uint4 bk = pend_bucket;
-    const uint32_t x = pend_x;
-    int q = -1;
-    if (bk.w == x) q = 3;
-    if (bk.z == x) q = 2;
-    if (bk.y == x) q = 1;
-    if (bk.x == x) q = 0;
-    bool found = act && q >= 0;
-    uint32_t slot = pend_b * BUCKET + q;
-    // Full home bucket without the seed (about 1 probe in 600): it may have
-    // spilled into the following buckets.
-    const bool full = bk.x != SEED_EMPTY && bk.y != SEED_EMPTY && bk.z != SEED_EMPTY &&
-                      bk.w != SEED_EMPTY;
-    if (__any_sync(FULL_MASK, act && !found && full)) {
-      if (act && !found && full) {
-        uint32_t b = pend_b;
-        while (true) {
-          b = (b + 1) & P.st.bucket_mask;
-          const uint4 nb = ldg_v4_hint(reinterpret_cast<const uint4 *>(P.st.seeds) + b, keep);
-          const uint32_t v[4] = {nb.x, nb.y, nb.z, nb.w};
-          bool open = false;
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            if (v[i] == x) { found = true; slot = b * BUCKET + i; }
-            if (v[i] == SEED_EMPTY) open = true;
-          }
-          if (found || open) break;
-        }
+  // ---- stage B helpers ------------------------------------------------------------
+  // ptxas puts every global load of the loop on one scoreboard, so the first use of the
+  // prefetched next tile would also wait for whatever table loads were issued after it -
+  // a full L2 round trip per tile.  Settle the prefetch (issued a whole stage A ago) BEFORE
+  // issuing table loads: the empty asm makes its words plain register values from here on.
+  __device__ __forceinline__ static void settle(uint32_t (&r)[5]) {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]));
+  }
+
+  // Slow half of a seed-table lookup: the home slot holds another seed and carries
+  // ST_MOVED_BIT, so the seed may sit further along (linear probing, ends at a free slot).
+  __device__ __forceinline__ bool walk(uint32_t x, uint32_t &slot) const {
+    uint32_t b = slot;
+    while (true) {
+      b = (b + 1) & P.st.slot_mask;
+      const uint32_t v = ldg_u32_hint(P.st.seeds + b, keep);
+      if ((v & ST_SEED_BITS) == x) {
+        slot = b;
+        return true;
       }
-    }
-    pend_n = 0;
-    const uint32_t bal = __ballot_sync(FULL_MASK, found);
-    if (bal) {
-      if (found) cq[(ct + __popc(bal & lt_mask)) & (CQ_CAP - 1)] = (uint64_t)slot << 32 | pend_p;
-      ct += __popc(bal);
-      if (PROF && found) n_seed++;
-      __syncwarp();
-      if (ct - ch >= 32) stage_c(32);
+      if (v & ST_FREE_BIT) return false;
     }
   }
 
-  // ---- stage B, first half: start the exact check of hits [first, first + n) ------
+  // Queue the lanes' verified seeds (seed-table slot, stream position) for stage C.
+  __device__ __forceinline__ void push_verified(bool found, uint32_t slot, uint32_t p) {
+#if DKB_X == 6
+    found = found && p == 0xFFFFFFFFu;  // timing experiment: no stage C
+#endif
+    const uint32_t bal = __ballot_sync(FULL_MASK, found);
+    if (bal == 0) return;
+    if (found) cq[(ct + __popc(bal & lt_mask)) & (CQ_CAP - 1)] = (uint64_t)slot << 32 | p;
+    ct += __popc(bal);
+    if (PROF && found) n_seed++;
+    __syncwarp();
+    if (ct - ch >= 32) stage_c(32);
+  }
+
+  // ---- stage B, lane-local form (strides 2 and 4) -----------------------------------
+  // Every lane verifies its OWN filter hits: no compaction, no shuffles, no id list.  Round
+  // r takes the lane's r-th hit of the tile, cuts its seed out of the lane's registers and
+  // issues the 4-byte load of the seed's home slot; the loads are looked at one tile later
+  // (after the next stage A), so L2 latency hides inside the warp.  A tile has ~1 hit per
+  // lane, the busiest lane 3-4; lanes beyond NR hits (rare) finish synchronously.
+  static constexpr int NR = 4;
+  uint32_t lv[NR] = {ST_EMPTY, ST_EMPTY, ST_EMPTY, ST_EMPTY};  // loaded home-slot words
+  uint32_t lx[NR] = {0, 0, 0, 0};                              // their seeds
+  uint32_t lidx = 0, lbase = 0;  // hit-mask bit of round r in byte r; the tile's first position
+
+  // Seed of the lookup whose hit bit is bit b of the tile's mask (lookup i = 31 - b starts
+  // i * D positions into the lane's chunk).
+  __device__ __forceinline__ uint32_t cut_seed(const uint32_t (&w)[5], uint32_t b) const {
+    constexpr uint32_t HI = D == 4 ? 8u : 16u, LO = D == 4 ? 4u : 8u;  // bits of b above the word index
+    // word index c = ((31 - b) * D) >> 4, taken from the inverted bits of b
+    uint32_t a0 = w[2], a1 = w[3], a2 = w[4];
+    if (b & HI) { a0 = w[0]; a1 = w[1]; a2 = w[2]; }
+    uint32_t lo = a1, hi = a2;
+    if (b & LO) { lo = a0; hi = a1; }
+    // shift = 2 * ((31 - b) * D mod 16) = (62 D - 2 D b) mod 32: the funnel shift wraps
+    return __funnelshift_r(lo, hi, 62u * D - 2u * D * b) & P.seed_mask;
+  }
+
+  // after = a value computed by the work that must come BEFORE the loaded words are looked
+  // at (the hit mask of the stage A that ran meanwhile).  The comparison mask is made to
+  // depend on it through a run-time zero; otherwise ptxas hoists these compares to the top
+  // of that stage A, where they wait for the scoreboard of loads issued a moment earlier.
+  __device__ __forceinline__ void resolve_local(uint32_t after) {
+    const uint32_t msk = ST_SEED_BITS + (after & zero);  // a sum: no known bits to split off
+    // bit r: round r's slot holds the seed, or says the seed may have moved on
+    uint32_t mm = 0;
+#pragma unroll
+    for (int r = 0; r < NR; r++)
+      mm |= (uint32_t)(((lv[r] ^ lx[r]) & msk) == 0 || (lv[r] & ~msk) != 0) << r;
+    if (!__any_sync(FULL_MASK, mm != 0)) return;
+    // About every second tile (a true seed somewhere in the warp).  One rolled copy of the
+    // code: each lane takes its lowest flagged round, whichever that is.
+    do {
+      const bool has = mm != 0;
+      const int r = has ? __ffs(mm) - 1 : 0;
+      mm &= mm - 1;
+      uint32_t v = lv[0], x = lx[0];
+      if (r == 1) { v = lv[1]; x = lx[1]; }
+      if (r == 2) { v = lv[2]; x = lx[2]; }
+      if (r == 3) { v = lv[3]; x = lx[3]; }
+      const uint32_t i = 31u - ((lidx >> (8 * r)) & 31u);
+      bool found = has && ((v ^ x) & ST_SEED_BITS) == 0;
+      const bool moved = has && !found;  // flagged without a match: ST_MOVED_BIT
+      uint32_t slot = seed_home(x, P.st.shift);
+      if (__any_sync(FULL_MASK, moved)) {
+        if (moved) found = walk(x, slot);
+        __syncwarp();
+      }
+      push_verified(found, slot, lbase + lane * CHUNK + i * D);
+    } while (__any_sync(FULL_MASK, mm != 0));
+  }
+
+  // Start the rounds of the tile whose words are w and whose hit mask is acc (bit 31 =
+  // lookup 0).  Any earlier rounds must have been resolved.
+  __device__ __forceinline__ void start_local(uint32_t acc, const uint32_t (&w)[5],
+                                              uint32_t tile_base) {
+#pragma unroll
+    for (int r = 0; r < NR; r++) lv[r] = ST_EMPTY;
+    if (PROF) n_bloom += __popc(acc);
+    uint32_t a = acc;  // bit 31 = lookup 0
+    lbase = tile_base;
+    while (true) {
+      lidx = 0;
+#pragma unroll
+      for (int r = 0; r < NR; r++) {
+        if (!__any_sync(FULL_MASK, a != 0)) break;
+        const bool has = a != 0;
+        const uint32_t b = 31u - __clz(a);  // any hit will do: take the highest bit
+        a &= ~(1u << (b & 31));
+        const uint32_t x = cut_seed(w, b);
+        lx[r] = x;
+#if DKB_X == 3
+        if (has) lv[r] = ldg_u32_hint(P.st.seeds + (seed_home(x, P.st.shift) & 0), keep);
+#elif DKB_X == 4
+        if (has) lv[r] = ldg_u32_hint(P.st.seeds + (seed_home(x, P.st.shift) & 4095), keep);
+#elif DKB_X == 5
+        if (has) lv[r] = ldg_u32_hint(P.st.seeds + (seed_home(x, P.st.shift) & 0x3FFFF), keep);
+#elif DKB_X != 1
+        if (has) lv[r] = ldg_u32_hint(P.st.seeds + seed_home(x, P.st.shift), keep);
+#endif
+        lidx |= (b & 31) << (8 * r);
+      }
+      if (!__any_sync(FULL_MASK, a != 0)) break;
+      // a lane with more than NR hits in one tile (rare): finish these rounds now
+      resolve_local(a);
+#pragma unroll
+      for (int r = 0; r < NR; r++) lv[r] = ST_EMPTY;
+    }
+  }
+
+  // ---- stage B, batch form (strides 1, 8, 16), second half: use the slots loaded one
+  // batch ago
+  // (after: see resolve_local)
+  __device__ __forceinline__ void consume_pending(uint32_t after) {
+    if (pend_n == 0) return;
+    const bool act = (uint32_t)lane < pend_n;
+    const uint32_t msk = ST_SEED_BITS + (after & zero);
+    const uint32_t v = pend_v, x = pend_x;
+    bool found = act && ((v ^ x) & msk) == 0;
+    const bool moved = act && !found && (v & ~msk) != 0;
+    uint32_t slot = pend_b;
+    if (__any_sync(FULL_MASK, moved)) {
+      if (moved) found = walk(x, slot);
+      __syncwarp();
+    }
+    pend_n = 0;
+    push_verified(found, slot, pend_p);
+  }
+
+  // ---- stage B, batch form, first half: start the exact check of hits [first, first + n)
   // Each lane takes one hit id, pulls the 16 bases at that position out of the
   // owning lane's registers with shuffles (no trip back to L2) and issues the
-  // load of the seed's bucket.  tile_base = stream position of lane 0's chunk.
+  // load of the seed's home slot.  tile_base = stream position of lane 0's chunk.
   __device__ __forceinline__ void issue_probes(uint32_t first, uint32_t n, const uint32_t (&w)[5],
                                                uint32_t tile_base) {
     const bool act = (uint32_t)lane < n;
     const uint32_t id = act ? hl[first + lane] : (uint32_t)lane << 6;
     const int src = id >> 6;
+    pend_v = ST_EMPTY;
     if constexpr (MACRO) {
       // macro tiles (strides 8, 16): the lookup index runs over SUB sub-tiles whose words
       // are no longer in registers; hits are rare here, so re-read them from L2
@@ -177,8 +291,8 @@ struct ScanWarp {
       pend_p = tile_base + (idx / LPT) * WTILE + src * CHUNK + (idx % LPT) * D;
       const uint32_t wi = pend_p >> 4;
       pend_x = __funnelshift_r(ld_bases(wi), ld_bases(wi + 1), 2 * (pend_p & 15)) & P.seed_mask;
-      pend_b = seed_bucket(pend_x, P.st.shift);
-      if (act) pend_bucket = ldg_v4_hint(reinterpret_cast<const uint4 *>(P.st.seeds) + pend_b, keep);
+      pend_b = seed_home(pend_x, P.st.shift);
+      if (act) pend_v = ldg_u32_hint(P.st.seeds + pend_b, keep);
       pend_n = n;
       return;
     }
@@ -193,8 +307,8 @@ struct ScanWarp {
     if (c == 3) { lo = v[3]; hi = v[4]; }
     pend_x = __funnelshift_r(lo, hi, 2 * (q & 15)) & P.seed_mask;
     pend_p = tile_base + src * CHUNK + q;
-    pend_b = seed_bucket(pend_x, P.st.shift);
-    if (act) pend_bucket = ldg_v4_hint(reinterpret_cast<const uint4 *>(P.st.seeds) + pend_b, keep);
+    pend_b = seed_home(pend_x, P.st.shift);
+    if (act) pend_v = ldg_u32_hint(P.st.seeds + pend_b, keep);
     pend_n = n;
   }
 
@@ -244,7 +358,7 @@ struct ScanWarp {
         }
         __syncwarp();
         for (uint32_t r = 0; r < total; r += 32) {
-          consume_pending();  // at most one batch of probes in flight
+          consume_pending(0);  // at most one batch of probes in flight
           issue_probes(r, min(total - r, 32u), w, tile_base);
         }
         __syncwarp();
@@ -273,7 +387,7 @@ struct ScanWarp {
       __syncwarp();
       const uint32_t here = min(total - base, (uint32_t)HL_CAP);
       for (uint32_t r = 0; r < here; r += 32) {
-        consume_pending();  // at most one batch of probes in flight
+        consume_pending(0);  // at most one batch of probes in flight
         issue_probes(r, min(here - r, 32u), w, tile_base);
       }
       __syncwarp();
@@ -281,8 +395,44 @@ struct ScanWarp {
   }
 
   __device__ __forceinline__ void drain() {
-    consume_pending();
+    if constexpr (LOCAL) resolve_local(0); else consume_pending(0);
     while (ct != ch) stage_c(min(ct - ch, 32u));
+  }
+
+  // bit * 2^e + a as ONE multiply-add (in C the compiler, knowing bit is 0 or 1, makes it a
+  // compare, a select and an add - three ALU-pipe instructions)
+  __device__ __forceinline__ uint32_t mad_pw(uint32_t bit, int e, uint32_t a) const {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(bit), "r"(P.pw[e]), "r"(a));
+    return r;
+  }
+
+  // One filter lookup of the s-mer whose bases start at the low bits of x: 1 when every
+  // filter bit of x is set (layout: bloom_bits() in dkb_device.cuh).  Issue cost on sm_100
+  // (scripts/micro/int_pipes.cu): ALU-pipe and FMA-pipe instructions take 2 cycles per warp
+  // each and overlap; IMAD.WIDE 2.4; a multiply-high 5 and it holds up the ALU pipe, so
+  // there is none here.  ALU: cut (caller), index shift, one shift per filter bit, AND.
+  // FMA: hash, wide multiply, address, and the caller's accumulate.
+  __device__ __forceinline__ uint32_t lookup(uint32_t x, uint32_t mult, uint32_t fbase) const {
+    const uint32_t h = x * mult;
+    unsigned long long prod;  // forced wide: ptxas would turn a plain (u64)h * n >> 32 into IMAD.HI
+    uint32_t word;
+    if constexpr (GF) {
+      // large candidate sets: the filter does not fit in shared memory; probe it in L2
+      asm("mul.wide.u32 %0, %1, %2;" : "=l"(prod) : "r"(h), "r"(P.bloom_words));
+      word = ldg_u32_hint(P.bloom + (uint32_t)(prod >> 32), keep);
+    } else {
+      asm("mul.wide.u32 %0, %1, %2;" : "=l"(prod) : "r"(h), "r"(P.filter_words));
+      // byte address = idx * 4 + base as a multiply-add (P.four is opaque), not an ALU-pipe LEA
+      const uint32_t addr = (uint32_t)(prod >> 32) * P.four + fbase;
+      asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(addr));
+    }
+    const uint32_t lo = (uint32_t)prod;
+    uint32_t bit = __funnelshift_r(word, 0, x);  // the shift wraps: bit (x & 31) comes down to bit 0
+    if (NH >= 2) bit &= __funnelshift_r(word, 0, lo >> 27);
+    if (NH >= 3) bit &= __funnelshift_r(word, 0, lo >> 22);
+    if (NH >= 4) bit &= __funnelshift_r(word, 0, lo >> 17);
+    return bit & 1u;
   }
 
   // ---- stage A, macro-tile form: LPT lookups of one sub-tile, hit bits in the low bits,
@@ -292,24 +442,13 @@ struct ScanWarp {
     const uint32_t mult = P.seed_mult;
     const uint32_t fbase = (uint32_t)__cvta_generic_to_shared(filt);
     uint32_t a = 0;
+    int n = 0;
 #pragma unroll
     for (int c = 0; c < 4; c++) {
 #pragma unroll
-      for (int t = 0; t < 16; t += D) {
+      for (int t = 0; t < 16; t += D, n++) {
         const uint32_t x = t ? __funnelshift_r(w[c], w[c + 1], 2 * t) : w[c];
-        const uint32_t h = x * mult;
-        uint32_t word;
-        if constexpr (GF) {
-          word = ldg_u32_hint(P.bloom + __umulhi(h, P.bloom_words), keep);
-        } else {
-          const uint32_t addr = __umulhi(h, (uint32_t)BLOOM_WORDS) * P.four + fbase;
-          asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(addr));
-        }
-        uint32_t bit = word << (x & 31);
-        if (NH >= 2) bit &= word << (__umulhi(h, SEED_MULT2) & 31);
-        if (NH >= 3) bit &= word << (__umulhi(h, SEED_MULT3) & 31);
-        if (NH >= 4) bit &= word << (__umulhi(h, SEED_MULT4) & 31);
-        a = __funnelshift_l(bit, a, 1);
+        a = mad_pw(lookup(x, mult, fbase), LPT - 1 - n, a);
       }
     }
     return a;
@@ -322,38 +461,28 @@ struct ScanWarp {
                                           uint32_t &acc1) const {
     const uint32_t mult = P.seed_mult;
     const uint32_t fbase = (uint32_t)__cvta_generic_to_shared(filt);
-    uint32_t part[4];  // per-word hit bits (16 / D each): four short dependency chains
+    // Lookup n of the tile puts its hit bit at bit 31 - n of the mask (D == 1: of acc0 for
+    // n < 32, of acc1 after) with a multiply-add by 2^(31 - n) from the parameter block -
+    // the FMA pipe has the room, and a literal power of two would become an ALU-pipe shift.
+    // Four chains, one per word.
+    constexpr int NB = 16 / D;  // lookups per word
+    uint32_t part[4];
 #pragma unroll
     for (int c = 0; c < 4; c++) {
       uint32_t a = 0;
 #pragma unroll
       for (int t = 0; t < 16; t += D) {
         const uint32_t x = t ? __funnelshift_r(w[c], w[c + 1], 2 * t) : w[c];
-        const uint32_t h = x * mult;
-        uint32_t word;
-        if constexpr (GF) {
-          // large candidate sets: the filter does not fit in shared memory; probe it in L2
-          word = ldg_u32_hint(P.bloom + __umulhi(h, P.bloom_words), keep);
-        } else {
-          // byte address = idx * 4 + base as a multiply-add (P.four is opaque), not an ALU-pipe LEA
-          const uint32_t addr = __umulhi(h, (uint32_t)BLOOM_WORDS) * P.four + fbase;
-          asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(addr));
-        }
-        uint32_t bit = word << (x & 31);
-        if (NH >= 2) bit &= word << (__umulhi(h, SEED_MULT2) & 31);
-        if (NH >= 3) bit &= word << (__umulhi(h, SEED_MULT3) & 31);
-        if (NH >= 4) bit &= word << (__umulhi(h, SEED_MULT4) & 31);
-        a = __funnelshift_l(bit, a, 1);
+        const int n = (c * NB + t / D) & 31;
+        a = mad_pw(lookup(x, mult, fbase), 31 - n, a);
       }
       part[c] = a;
     }
-    // lookup 0 ends up in bit 31 of acc0
-    constexpr int NB = 16 / D;  // hit bits per word
     if constexpr (D == 1) {
-      acc0 = part[0] << 16 | part[1];
-      acc1 = part[2] << 16 | part[3];
+      acc0 = part[0] + part[1];
+      acc1 = part[2] + part[3];
     } else {
-      acc0 = (part[0] << (3 * NB) | part[1] << (2 * NB) | part[2] << NB | part[3]) << (32 - 4 * NB);
+      acc0 = part[0] + part[1] + part[2] + part[3];
       acc1 = 0;
     }
   }
@@ -458,7 +587,12 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
         acc = acc << LPT | W.stage_a_sub(w);
       }
       if (last_group) {
-        W.consume_pending();
+        W.consume_pending(acc);
+        // same scoreboard trap as in the tile path: settle the prefetched group first
+#pragma unroll
+        for (int j = 0; j < GS; j++)
+          asm volatile("" : "+r"(nxt[j].x), "+r"(nxt[j].y), "+r"(nxt[j].z), "+r"(nxt[j].w));
+        asm volatile("" : "+r"(nxt_edge));
         const uint32_t w0[5] = {0, 0, 0, 0, 0};
         W.handle_hits(acc, 0, w0, cur_macro * SUB * WTILE);
         acc = 0;
@@ -468,6 +602,30 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
   uint32_t tile = warp * gridDim.x + blockIdx.x;  // consecutive tiles on different SMs
   uint32_t nxt[5];
   if (tile < P.n_tiles) load_tile(P, tile, lane, nxt);
+  if constexpr (ScanWarp<D, NH, GF, PROF>::LOCAL) {
+    // Rotated loop: the table loads of tile t (its rounds) are issued at the top of
+    // iteration t + 1, right after the prefetched words of tile t + 1 have been settled and
+    // before tile t + 2 is requested; they are looked at after stage A of tile t + 1.  The
+    // loop's back edge thus falls where no load is in flight (ptxas waits for the shared
+    // scoreboard there).
+    uint32_t w[5] = {0, 0, 0, 0, 0};
+    uint32_t acc_prev = 0, base_prev = 0;
+    for (; tile < P.n_tiles; tile += n_warps) {
+      W.settle(nxt);
+#if DKB_X != 2
+      W.start_local(acc_prev, w, base_prev);
+#endif
+#pragma unroll
+      for (int i = 0; i < 5; i++) w[i] = nxt[i];
+      if (tile + n_warps < P.n_tiles) load_tile(P, tile + n_warps, lane, nxt);
+      halo_finish(lane, w);
+      uint32_t acc1;
+      W.stage_a(w, acc_prev, acc1);
+      W.resolve_local(acc_prev);
+      base_prev = tile * WTILE;
+    }
+    W.start_local(acc_prev, w, base_prev);  // the last tile's hits; drain() resolves them
+  } else {
   for (; tile < P.n_tiles; tile += n_warps) {
     uint32_t w[5];
 #pragma unroll
@@ -476,8 +634,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
     halo_finish(lane, w);
     uint32_t acc0, acc1;
     W.stage_a(w, acc0, acc1);
-    W.consume_pending();  // the previous tile's seed buckets have had a whole stage A to arrive
+    W.consume_pending(acc0 | acc1);
+    W.settle(nxt);
     W.handle_hits(acc0, acc1, w, tile * WTILE);
+  }
   }
   }
   W.drain();
