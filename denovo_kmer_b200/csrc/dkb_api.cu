@@ -40,7 +40,8 @@ struct dkb_ctx {
   uint4 *d_tslots = nullptr;
   uint32_t table_slots = 0;
   // seeds
-  uint32_t *d_seeds = nullptr, *d_sinfo = nullptr;
+  uint32_t *d_seeds = nullptr, *d_sid = nullptr;
+  uint4 *d_srec = nullptr;  // seed records, 2 x uint4 per seed
   uint32_t seed_slots = 0;
   uint32_t n_seeds = 0;
   uint32_t *d_bloom = nullptr;
@@ -114,7 +115,7 @@ void dfree(T *&p) {
 void free_table(dkb_ctx *c) {
   dfree(c->d_keys); dfree(c->d_variant); dfree(c->d_allele); dfree(c->d_dead);
   dfree(c->d_tslots);
-  dfree(c->d_seeds); dfree(c->d_sinfo); dfree(c->d_bloom);
+  dfree(c->d_seeds); dfree(c->d_sid); dfree(c->d_srec); dfree(c->d_bloom);
   dfree(c->d_counts); dfree(c->d_hits); dfree(c->d_distinct); dfree(c->d_nkmers);
   dfree(c->d_calls);
   c->n_entries = c->n_live = 0;
@@ -254,7 +255,8 @@ void collect_timing(dkb_ctx *ctx) {
 SeedTable seed_table(const dkb_ctx *ctx) {
   SeedTable T;
   T.seeds = ctx->d_seeds;
-  T.sinfo = ctx->d_sinfo;
+  T.sid = ctx->d_sid;
+  T.rec = ctx->d_srec;
   T.slot_mask = ctx->seed_slots - 1;
   T.shift = 32 - log2_u32(ctx->seed_slots);
   return T;
@@ -496,10 +498,10 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
   ctx->table_slots = pow2_at_least((uint64_t)slots_per_entry * n + 2);  // <= 0.25 entries per 2-slot bucket
   uint16_t *d_wi = nullptr, *d_wc = nullptr;
   uint32_t *d_slot_of = nullptr;
-  uint32_t *d_set = nullptr;
+  uint32_t *d_set = nullptr, *d_cov = nullptr;
   unsigned int *d_nseeds = nullptr;
   cudaStream_t st = ctx->s_scan;
-  auto cleanup = [&]() { dfree(d_wi); dfree(d_wc); dfree(d_slot_of); dfree(d_set); dfree(d_nseeds); };
+  auto cleanup = [&]() { dfree(d_wi); dfree(d_wc); dfree(d_slot_of); dfree(d_set); dfree(d_cov); dfree(d_nseeds); };
   rc = [&]() -> int {
     CU(cudaMalloc(&ctx->d_keys, n1 * 8));
     CU(cudaMalloc(&ctx->d_variant, n1 * 4));
@@ -544,16 +546,14 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
       k_insert_entries<<<g1, TB, 0, st>>>(B);
       k_mark_repeats<<<g1, TB, 0, st>>>(B);
       k_apply_dead<<<g1, TB, 0, st>>>(B);
-      k_assign_seeds<<<g2, TB, 0, st>>>(B, true, d_set, set_slots - 1, d_nseeds, SeedTable{},
-                                        nullptr, 0, seed_mult, ctx->NH);
+      k_assign_seeds<<<g2, TB, 0, st>>>(B, ASSIGN_COUNT, d_set, set_slots - 1, d_nseeds, SeedTable{},
+                                        nullptr, nullptr, 0, seed_mult, ctx->NH);
       CU(cudaGetLastError());
     }
     unsigned int n_seeds = 0;
     CU(cudaMemcpyAsync(&n_seeds, d_nseeds, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     ctx->n_seeds = n_seeds;
-    // At most 1/16 full (1/8 for large seed sets, which must still fit L2): a filter false
-    // positive lands on a slot marked ST_MOVED_BIT (second load) once in several hundred probes.
     // At most 1/8 full: a filter false positive lands on a slot marked ST_MOVED_BIT (second
     // load) about once in a hundred probes; 16 slots per seed halve that but cost more L2
     // (measured 2-7 % slower at every stride).
@@ -561,15 +561,28 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
     if (const char *e = getenv("DKB_SEED_SLOTS_PER_SEED")) per_seed = atoi(e) > 1 ? atoi(e) : per_seed;
     ctx->seed_slots = pow2_at_least((uint64_t)per_seed * n_seeds + 2);
     CU(cudaMalloc(&ctx->d_seeds, (size_t)ctx->seed_slots * 4));
-    CU(cudaMalloc(&ctx->d_sinfo, (size_t)ctx->seed_slots * 4));
+    CU(cudaMalloc(&ctx->d_sid, (size_t)ctx->seed_slots * 4));
+    const size_t ns1 = n_seeds ? n_seeds : 1;
+    CU(cudaMalloc(&ctx->d_srec, ns1 * 32));
+    CU(cudaMalloc(&d_cov, ns1 * 12));
+    CU(cudaMemsetAsync(d_cov, 0, ns1 * 12, st));
+    CU(cudaMemsetAsync(d_nseeds, 0, 4, st));  // reused as the numbering counter
     CU(cudaMemsetAsync(ctx->d_seeds, 0x40, (size_t)ctx->seed_slots * 4, st));  // ST_EMPTY
-    CU(cudaMemsetAsync(ctx->d_sinfo, 0, (size_t)ctx->seed_slots * 4, st));
+    CU(cudaMemsetAsync(ctx->d_sid, 0, (size_t)ctx->seed_slots * 4, st));
     ctx->bloom_words = ctx->gf ? l2_filter_words((double)n_seeds) / 4 * 4 : (uint32_t)BLOOM_WORDS;
     CU(cudaMalloc(&ctx->d_bloom, (size_t)ctx->bloom_words * 4));
     CU(cudaMemsetAsync(ctx->d_bloom, 0, (size_t)ctx->bloom_words * 4, st));
     if (n) {
-      k_assign_seeds<<<g2, TB, 0, st>>>(B, false, nullptr, 0, nullptr, seed_table(ctx),
+      const SeedTable T = seed_table(ctx);
+      k_assign_seeds<<<g2, TB, 0, st>>>(B, ASSIGN_INSERT, nullptr, 0, nullptr, T, nullptr,
                                         ctx->d_bloom, ctx->bloom_words, seed_mult, ctx->NH);
+      k_number_seeds<<<(ctx->seed_slots + TB - 1) / TB, TB, 0, st>>>(T, ctx->seed_slots, d_nseeds);
+      k_init_records<<<(uint32_t)((ns1 * 8 + TB - 1) / TB), TB, 0, st>>>(
+          reinterpret_cast<uint32_t *>(ctx->d_srec), n_seeds);
+      k_assign_seeds<<<g2, TB, 0, st>>>(B, ASSIGN_RECORD, nullptr, 0, nullptr, T, d_cov,
+                                        ctx->d_bloom, ctx->bloom_words, seed_mult, ctx->NH);
+      k_finish_records<<<(uint32_t)((ns1 + TB - 1) / TB), TB, 0, st>>>(
+          reinterpret_cast<uint32_t *>(ctx->d_srec), d_cov, n_seeds);
       CU(cudaGetLastError());
     }
     std::vector<uint32_t> bloom(ctx->bloom_words);

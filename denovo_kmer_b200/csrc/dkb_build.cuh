@@ -75,9 +75,9 @@ __global__ void k_apply_dead(const BuildParams B) {
   if (B.dead[i]) B.kt.slots[B.slot_of[i]].z = ENTRY_DEAD;
 }
 
-// Insert (seed, offset bit) into the seed table: the home slot, else the first free slot
-// after it, with the home slot marked ST_MOVED_BIT so that lookups know to walk on.
-__device__ __forceinline__ void seedtab_insert(const SeedTable &T, uint32_t seed, uint32_t info) {
+// Insert a seed into the seed table: the home slot, else the first free slot after it,
+// with the home slot marked ST_MOVED_BIT so that lookups know to walk on.
+__device__ __forceinline__ void seedtab_insert(const SeedTable &T, uint32_t seed) {
   uint32_t slot = seed_home(seed, T.shift);
   bool home = true;
   while (true) {
@@ -86,13 +86,63 @@ __device__ __forceinline__ void seedtab_insert(const SeedTable &T, uint32_t seed
       old = atomicCAS(T.seeds + slot, ST_EMPTY, seed);
       if (old == ST_EMPTY) old = seed;
     }
-    if ((old & ST_SEED_BITS) == seed) {
-      atomicOr(T.sinfo + slot, info);
-      return;
-    }
+    if ((old & ST_SEED_BITS) == seed) return;
     if (home) atomicOr(T.seeds + slot, ST_MOVED_BIT);  // taken by another seed
     home = false;
     slot = (slot + 1) & T.slot_mask;
+  }
+}
+
+// Slot of a seed that is in the table.
+__device__ __forceinline__ uint32_t seedtab_find(const SeedTable &T, uint32_t seed) {
+  uint32_t slot = seed_home(seed, T.shift);
+  while ((T.seeds[slot] & ST_SEED_BITS) != seed) slot = (slot + 1) & T.slot_mask;
+  return slot;
+}
+
+// Number the occupied slots 0 .. n_seeds - 1 (any order).
+__global__ void k_number_seeds(const SeedTable T, uint32_t n_slots, unsigned int *counter) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n_slots) return;
+  if (!(T.seeds[slot] & ST_FREE_BIT)) T.sid[slot] = atomicAdd(counter, 1u);
+}
+
+// Working form of a seed record while the designations are being collected (same 8 words):
+// {info, OR of the windows' bases [3], AND of (bases | not covered) [3], unused}; cov[3] per
+// seed = union of the windows' extents.  k_finish_records turns it into the final form.
+__device__ __forceinline__ void record_add(uint32_t *rec, uint32_t *cov, int j, uint64_t v, int k,
+                                           int E) {
+  atomicOr(rec, 1u << j);
+  if (E + k > NB_BASES) return;  // neighbourhood does not fit: records stay all-wild
+  const int o = E - j;           // first base of the window inside the neighbourhood
+  const unsigned __int128 val = (unsigned __int128)v << (2 * o);
+  const unsigned __int128 ext = (unsigned __int128)kmer_mask(k) << (2 * o);
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const uint32_t vw = (uint32_t)(val >> (32 * i)), ew = (uint32_t)(ext >> (32 * i));
+    if (ew == 0) continue;
+    atomicOr(rec + 1 + i, vw);
+    atomicAnd(rec + 4 + i, vw | ~ew);
+    atomicOr(cov + i, ew);
+  }
+}
+
+__global__ void k_init_records(uint32_t *rec, uint32_t n_seeds) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_seeds * 8u) return;
+  const uint32_t w = i & 7;
+  rec[i] = w >= 4 && w <= 6 ? 0xFFFFFFFFu : 0u;
+}
+
+__global__ void k_finish_records(uint32_t *rec, const uint32_t *cov, uint32_t n_seeds) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_seeds) return;
+  uint32_t *r = rec + (size_t)i * 8;
+#pragma unroll
+  for (int w = 0; w < 3; w++) {
+    const uint32_t d = r[1 + w] ^ r[4 + w];               // bases on which the windows disagree
+    const uint32_t t = (d | d >> 1) & 0x55555555u;
+    r[4 + w] = ~cov[(size_t)i * 3 + w] | t | t << 1;      // wild: not covered, or disagreement
   }
 }
 
@@ -118,10 +168,13 @@ __device__ __forceinline__ void seedset_insert(uint32_t *set, uint32_t mask, uin
 //     G = floor((k-s+1)/D)*D along the haplotype, so neighbouring windows share
 //     them (2 seeds per SNV haplotype strand and class at k=31, s<=15);
 //   min-hash rule (no hints): the s-mer of the class with the smallest hash.
-// count_only: just add the seeds to `set` (sizing pass); otherwise record the
-// offsets in the entry's slot, insert the seeds and set their filter bits.
-__global__ void k_assign_seeds(const BuildParams B, bool count_only, uint32_t *set,
-                               uint32_t set_mask, unsigned int *n_seeds, const SeedTable T,
+// Three passes (the choice of offsets is the same in each):
+//   ASSIGN_COUNT   add the seeds to `set` (sizing);
+//   ASSIGN_INSERT  record the offsets in the entry's slot, insert the seeds, set their filter bits;
+//   ASSIGN_RECORD  (seeds numbered by k_number_seeds) add offset and window to the seed's record.
+enum { ASSIGN_COUNT = 0, ASSIGN_INSERT = 1, ASSIGN_RECORD = 2 };
+__global__ void k_assign_seeds(const BuildParams B, int pass, uint32_t *set, uint32_t set_mask,
+                               unsigned int *n_seeds, const SeedTable T, uint32_t *cov,
                                uint32_t *bloom, uint32_t bloom_words, uint32_t seed_mult,
                                int n_hashes) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -168,16 +221,19 @@ __global__ void k_assign_seeds(const BuildParams B, bool count_only, uint32_t *s
       }
     }
     const uint32_t seed = (uint32_t)(v >> (2 * j)) & smask;
-    if (count_only) {
+    if (pass == ASSIGN_COUNT) {
       seedset_insert(set, set_mask, seed, n_seeds);
-    } else {
+    } else if (pass == ASSIGN_INSERT) {
       offs |= (uint32_t)(j / D) << (W * (ori * D + c));
-      seedtab_insert(T, seed, 1u << j);
+      seedtab_insert(T, seed);
       const uint32_t h = seed * seed_mult;
       atomicOr(bloom + bloom_word(h, bloom_words), bloom_bits(seed, h, bloom_words, n_hashes));
+    } else {
+      const uint32_t id = T.sid[seedtab_find(T, seed)];
+      record_add(reinterpret_cast<uint32_t *>(T.rec) + (size_t)id * 8, cov + (size_t)id * 3, j, v, k, E);
     }
   }
-  if (!count_only) atomicOr(&B.kt.slots[B.slot_of[i]].w, offs);
+  if (pass == ASSIGN_INSERT) atomicOr(&B.kt.slots[B.slot_of[i]].w, offs);
 }
 
 // ---- kernel 3: finalise -----------------------------------------------------

@@ -112,15 +112,27 @@ __device__ __forceinline__ uint64_t ldg_u64_hint(const void *ptr, uint64_t pol) 
 
 // ---- the two lookup structures (both in L2) -----------------------------------
 // Seed table: one uint32 word per slot (see ST_*), open addressing, linear probing, at
-// most 1/8 full; sinfo[slot] = bitmap of the offsets j at which some key designates this
-// seed.  A lookup is ONE 4-byte load unless the home slot carries ST_MOVED_BIT (about one
-// slot in 400): a seed absent from an unmarked home slot is absent from the table.
+// most 1/8 full.  A lookup is ONE 4-byte load unless the home slot carries ST_MOVED_BIT
+// (about one slot in 100): a seed absent from an unmarked home slot is absent from the table.
+// sid[slot] = dense number of the seed; rec[number] = its 32-byte record (SeedRec).
 struct SeedTable {
   uint32_t *seeds;
-  uint32_t *sinfo;
+  uint32_t *sid;
+  uint4 *rec;          // 2 x uint4 per seed
   uint32_t slot_mask;  // n_slots - 1
   uint32_t shift;      // 32 - log2(n_slots)
 };
+// Seed record, 8 words: {info, nb[0..2], wild[0..2], 0}.
+//   info  bit j = some key designates this seed at offset j (its window starts j before the seed)
+//   nb    the NEIGHBOURHOOD: the 48 bases from E = k - s before the seed, 2 bits each, stream
+//         order - the union of all windows that designate the seed (needs 2k - s <= 48)
+//   wild  both bits of a base set where the designating keys disagree, or none covers it
+// A read window can equal a designating key only if the read equals nb on the window's
+// bases outside wild.  Stage C therefore compares the read with nb once (one 32-byte load)
+// and probes the key table only for windows inside the matching run around the seed: an
+// s-mer that equals a seed by chance (1 lookup in 1300 at s = 14 with 200 k seeds) costs a
+// compare instead of ~16 dependent key-table probes that miss L2.
+constexpr int NB_BASES = 48;
 // Key table: 16-byte slots {key lo, key hi, entry index, packed designated
 // offsets}, buckets of 2 slots = one 32-byte L2 sector (two LDG.128), a
 // multimap: one slot per (key, owner) entry; a full bucket spills into the next.

@@ -55,67 +55,148 @@ struct ScanWarp {
     return wi < P.n_mwords ? __ldg(P.mask + wi) : 0u;
   }
 
-  // ---- stage C: every candidate window of up to n verified seeds ----------------
-  // One lane per verified seed.  All windows of a seed at p lie in
-  // [p - (k - s), p + k): their bases and mask bits are fetched once (5 + 3
-  // words, issued together with the offset bitmap), then each window costs one
-  // key-bucket load.
+  // ---- stage C: the candidate windows of up to n verified seeds --------------------
+  // Key-table probe of one window: v = its k bases in stream order (first base least
+  // significant), j = the offset at which it would designate the seed that led here.
+  __device__ __forceinline__ void probe_window(uint64_t v, int j) {
+    const int k = P.k;
+    const uint64_t km = kmer_mask(k);
+    if (PROF) n_probe++;
+    const uint64_t fwd = base_reverse(v, k);
+    const uint64_t rc = ~v & km;  // complement of the stream-order value IS the rc key
+    const uint64_t key = fwd <= rc ? fwd : rc;
+    const int ori = fwd <= rc ? 0 : 1;
+    uint32_t bk = key_bucket(key, P.kt.bucket_mask);
+    while (true) {
+      const uint4 *bp = P.kt.slots + bk * KBUCKET;
+      const uint4 s0 = ldg_v4_hint(bp, keep), s1 = ldg_v4_hint(bp + 1, keep);
+      const uint64_t k0 = slot_key(s0), k1 = slot_key(s1);
+      if (k0 == key && s0.z != ENTRY_DEAD && slot_offset(s0.w, ori, j % D, D) == (uint32_t)j) {
+        atomicAdd(P.counts + s0.z, 1u);
+        if (PROF) n_hit++;
+      }
+      if (k1 == key && s1.z != ENTRY_DEAD && slot_offset(s1.w, ori, j % D, D) == (uint32_t)j) {
+        atomicAdd(P.counts + s1.z, 1u);
+        if (PROF) n_hit++;
+      }
+      if (k0 == KEY_EMPTY || k1 == KEY_EMPTY) break;  // bucket not full: nothing spilled
+      bk = (bk + 1) & P.kt.bucket_mask;
+    }
+  }
+
+  // Phase 1, one lane per verified seed.  All windows of a seed at p lie in
+  // [p - (k - s), p + k): their bases and mask bits are fetched once (5 + 3 words) together
+  // with the seed's number; then the seed's record (SeedRec, one 32-byte sector) says which
+  // offsets are designated and what the designating keys look like around the seed.  The
+  // read is compared with that neighbourhood once, invalid positions count as mismatches,
+  // and only windows inside the matching run around the seed survive.  A chance seed match
+  // (the common case on unrelated sequence) ends here.
+  // Phase 2, one lane per surviving window: the owners list (lane, offset) pairs in the ring
+  // slots just consumed, and the warp probes them 32 at a time - a seed's ~16 windows no
+  // longer cost one dependent L2 round trip each inside a single lane.
   __device__ __forceinline__ void stage_c(uint32_t n) {
+    const int k = P.k, s = P.s, E = k - s;
+    const uint64_t km = kmer_mask(k);
+    uint32_t info = 0, p = 0, rn0 = 0, rn1 = 0, rn2 = 0;
     if ((uint32_t)lane < n) {
       const uint64_t e = cq[(ch + lane) & (CQ_CAP - 1)];
-      const uint32_t p = (uint32_t)e;
-      const int k = P.k, E = k - P.s;
+      p = (uint32_t)e;
       const uint32_t start = p > (uint32_t)E ? p - (uint32_t)E : 0u;
       const uint32_t bw0 = start >> 4, mw0 = start >> 5;
-      uint32_t info = ldg_u32_hint(P.st.sinfo + (uint32_t)(e >> 32), keep);
+      const uint32_t id = ldg_u32_hint(P.st.sid + (uint32_t)(e >> 32), keep);
       uint32_t b[5], m[3];
 #pragma unroll
       for (int i = 0; i < 5; i++) b[i] = ld_bases(bw0 + i);
 #pragma unroll
       for (int i = 0; i < 3; i++) m[i] = ld_mask(mw0 + i);
-      const uint64_t km = kmer_mask(k);
-      const uint32_t vm = (1u << k) - 1;  // k <= 31
-      while (info) {
-        const int j = __ffs(info) - 1;
-        info &= info - 1;
-        if (p < (uint32_t)j) continue;
-        const uint32_t w = p - (uint32_t)j;
-        if (w + (uint32_t)k > P.n_pos) continue;
-        if (PROF) n_probe++;
-        // validity: mask bits w .. w+k-1 must all be set
-        const uint32_t mo = w - (mw0 << 5);  // < 64
-        const uint32_t mbits = mo < 32 ? __funnelshift_r(m[0], m[1], mo)
-                                       : __funnelshift_r(m[1], m[2], mo - 32);
-        if ((mbits & vm) != vm) continue;
-        // the window's bases in stream order (first base least significant)
-        const uint32_t bo = w - (bw0 << 4);  // < 48
-        uint32_t x0 = b[0], x1 = b[1], x2 = b[2];
-        if (bo >= 16) { x0 = b[1]; x1 = b[2]; x2 = b[3]; }
-        if (bo >= 32) { x0 = b[2]; x1 = b[3]; x2 = b[4]; }
-        const uint32_t sh = 2 * (bo & 15);
-        const uint64_t v =
-            ((uint64_t)__funnelshift_r(x1, x2, sh) << 32 | __funnelshift_r(x0, x1, sh)) & km;
-        const uint64_t fwd = base_reverse(v, k);
-        const uint64_t rc = ~v & km;  // complement of the stream-order value IS the rc key
-        const uint64_t key = fwd <= rc ? fwd : rc;
-        const int ori = fwd <= rc ? 0 : 1;
-        uint32_t bk = key_bucket(key, P.kt.bucket_mask);
-        while (true) {
-          const uint4 *bp = P.kt.slots + bk * KBUCKET;
-          const uint4 s0 = ldg_v4_hint(bp, keep), s1 = ldg_v4_hint(bp + 1, keep);
-          const uint64_t k0 = slot_key(s0), k1 = slot_key(s1);
-          if (k0 == key && s0.z != ENTRY_DEAD && slot_offset(s0.w, ori, j % D, D) == (uint32_t)j) {
-            atomicAdd(P.counts + s0.z, 1u);
-            if (PROF) n_hit++;
-          }
-          if (k1 == key && s1.z != ENTRY_DEAD && slot_offset(s1.w, ori, j % D, D) == (uint32_t)j) {
-            atomicAdd(P.counts + s1.z, 1u);
-            if (PROF) n_hit++;
-          }
-          if (k0 == KEY_EMPTY || k1 == KEY_EMPTY) break;  // bucket not full: nothing spilled
-          bk = (bk + 1) & P.kt.bucket_mask;
+      const uint4 r0 = ldg_v4_hint(P.st.rec + 2 * (size_t)id, keep);
+      const uint4 r1 = ldg_v4_hint(P.st.rec + 2 * (size_t)id + 1, keep);
+      info = r0.x;
+      if (p >= (uint32_t)E && E + k <= NB_BASES) {
+        // the read's neighbourhood (base 0 = p - E) and its mismatches, 2 bits per base
+        const uint32_t sh = 2 * (start & 15);
+        rn0 = __funnelshift_r(b[0], b[1], sh);
+        rn1 = __funnelshift_r(b[1], b[2], sh);
+        rn2 = __funnelshift_r(b[2], b[3], sh);
+        const uint32_t mm0 = (rn0 ^ r0.y) & ~r1.x, mm1 = (rn1 ^ r0.z) & ~r1.y, mm2 = (rn2 ^ r0.w) & ~r1.z;
+        const unsigned __int128 mm = (unsigned __int128)mm2 << 64 | (unsigned __int128)mm1 << 32 | mm0;
+        // invalid positions (N, low quality, read separators, end of stream), 1 bit per base
+        const uint32_t mo = start & 31;
+        uint64_t inv = ~((uint64_t)__funnelshift_r(m[1], m[2], mo) << 32 | __funnelshift_r(m[0], m[1], mo));
+        if (P.n_pos - start < (uint32_t)NB_BASES) inv |= ~0ull << (P.n_pos - start);  // end of stream
+        inv &= (1ull << NB_BASES) - 1;
+        // R = first bad base at or after the seed's end, Lm = last one before its start; nothing
+        // beyond base E + k is covered by a window, so both searches fit 64 bits
+        const uint64_t ma = (uint64_t)(mm >> (2 * (E + s))), mb = (uint64_t)mm & ((1ull << (2 * E)) - 1);
+        const uint64_t ia = inv >> (E + s), ib = inv & ((1ull << E) - 1);
+        int R = NB_BASES, Lm = -1;
+        if (ma) R = E + s + ((__ffsll((long long)ma) - 1) >> 1);
+        if (ia) R = min(R, E + s + __ffsll((long long)ia) - 1);
+        if (mb) Lm = (63 - __clzll((long long)mb)) >> 1;
+        if (ib) Lm = max(Lm, 63 - __clzll((long long)ib));
+        // window j covers bases [E - j, E - j + k): inside (Lm, R)  <=>  E + k - R <= j < E - Lm
+        const int jlo = E + k - R > 0 ? E + k - R : 0, jhi = E - Lm - 1;
+        info = jhi >= jlo ? info & ((2u << jhi) - 1u) & ~((1u << jlo) - 1u) : 0u;
+        if ((inv >> E) & ((1ull << s) - 1)) info = 0;  // an invalid base inside the seed itself
+      } else {
+        // no usable neighbourhood (stream start, or 2k - s > NB_BASES): every designated
+        // offset is checked here, one after the other
+        const uint32_t vm = (1u << k) - 1;  // k <= 31
+        while (info) {
+          const int j = __ffs(info) - 1;
+          info &= info - 1;
+          if (p < (uint32_t)j) continue;
+          const uint32_t w = p - (uint32_t)j;
+          if (w + (uint32_t)k > P.n_pos) continue;
+          const uint32_t wo = w - (mw0 << 5);  // < 64
+          const uint32_t mbits = wo < 32 ? __funnelshift_r(m[0], m[1], wo)
+                                         : __funnelshift_r(m[1], m[2], wo - 32);
+          if ((mbits & vm) != vm) continue;
+          const uint32_t bo = w - (bw0 << 4);  // < 48
+          uint32_t x0 = b[0], x1 = b[1], x2 = b[2];
+          if (bo >= 16) { x0 = b[1]; x1 = b[2]; x2 = b[3]; }
+          if (bo >= 32) { x0 = b[2]; x1 = b[3]; x2 = b[4]; }
+          const uint32_t sh = 2 * (bo & 15);
+          probe_window(((uint64_t)__funnelshift_r(x1, x2, sh) << 32 | __funnelshift_r(x0, x1, sh)) & km, j);
         }
       }
+    }
+    // ---- phase 2 ----
+    uint32_t cnt = __popc(info), incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(FULL_MASK, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const uint32_t total = __shfl_sync(FULL_MASK, incl, 31);
+    uint16_t *tl = reinterpret_cast<uint16_t *>(cq);  // task t lives in consumed ring slot ch + t / 4
+    constexpr uint32_t TL_CAP = 128;                  // 32 slots of 8 bytes
+    for (uint32_t base = 0; base < total; base += TL_CAP) {
+      uint32_t idx = incl - cnt - base;  // wraps below zero for tasks of earlier passes
+      uint32_t a = info;
+      while (a) {
+        const int j = __ffs(a) - 1;
+        a &= a - 1;
+        if (idx < TL_CAP) tl[((ch + (idx >> 2)) & (CQ_CAP - 1)) * 4 + (idx & 3)] = (uint16_t)(lane << 5 | j);
+        idx++;
+      }
+      __syncwarp();
+      const uint32_t here = min(total - base, TL_CAP);
+      for (uint32_t r = 0; r < here; r += 32) {
+        const uint32_t t = r + lane;
+        const bool act = t < here;
+        const uint32_t task = act ? tl[((ch + (t >> 2)) & (CQ_CAP - 1)) * 4 + (t & 3)] : 0u;
+        const int src = task >> 5, j = task & 31;
+        const uint32_t q0 = __shfl_sync(FULL_MASK, rn0, src), q1 = __shfl_sync(FULL_MASK, rn1, src),
+                       q2 = __shfl_sync(FULL_MASK, rn2, src);
+        if (act) {
+          const int o = E - j;  // first base of the window in the neighbourhood, 0 .. E
+          const uint32_t x0 = o < 16 ? q0 : q1, x1 = o < 16 ? q1 : q2, x2 = o < 16 ? q2 : 0u;
+          const uint32_t sh = 2 * (o & 15);
+          probe_window(((uint64_t)__funnelshift_r(x1, x2, sh) << 32 | __funnelshift_r(x0, x1, sh)) & km, j);
+        }
+      }
+      __syncwarp();
     }
     ch += n;
     __syncwarp();
