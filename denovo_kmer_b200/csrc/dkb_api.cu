@@ -44,7 +44,9 @@ struct dkb_ctx {
   uint4 *d_srec = nullptr;  // seed records, 2 x uint4 per seed
   uint32_t seed_slots = 0;
   uint32_t n_seeds = 0;
-  uint32_t *d_bloom = nullptr;
+  uint32_t *d_bloom = nullptr, *d_pre = nullptr;
+  uint32_t pre_words = 0;  // shared-memory pre-filter of the L2 filter mode
+  bool want_pre = false;   // the tuner's choice
   uint64_t bloom_bits_set = 0;
   // counters and results
   uint32_t *d_counts = nullptr;  // [3][n_entries]
@@ -115,7 +117,7 @@ void dfree(T *&p) {
 void free_table(dkb_ctx *c) {
   dfree(c->d_keys); dfree(c->d_variant); dfree(c->d_allele); dfree(c->d_dead);
   dfree(c->d_tslots);
-  dfree(c->d_seeds); dfree(c->d_sid); dfree(c->d_srec); dfree(c->d_bloom);
+  dfree(c->d_seeds); dfree(c->d_sid); dfree(c->d_srec); dfree(c->d_bloom); dfree(c->d_pre);
   dfree(c->d_counts); dfree(c->d_hits); dfree(c->d_distinct); dfree(c->d_nkmers);
   dfree(c->d_calls);
   c->n_entries = c->n_live = 0;
@@ -133,7 +135,20 @@ uint32_t l2_filter_words(double seeds) {
   if (w < BLOOM_WORDS) w = BLOOM_WORDS;
   return (uint32_t)w;
 }
-constexpr double L2_LOOKUP_CYCLES = 450.0;  // per lane lookup, fitted (profiles/README.md)
+// Shared-memory pre-filter of the L2 filter mode: 128 KB.  It must leave ~100 KB of L1, whose
+// lines track the outstanding L2 loads (192 KB of pre-filter: half the speed; profiles/README.md).
+constexpr uint32_t PRE_WORDS = 32768;
+
+// Words of the pre-filter the build should use for this table (0 = none).  DKB_PREFILTER_WORDS overrides.
+uint32_t pre_filter_words(bool want) {
+  if (const char *e = getenv("DKB_PREFILTER_WORDS")) {
+    long w = atol(e);
+    if (w < 0) w = 0;
+    if (w > BLOOM_WORDS) w = BLOOM_WORDS;
+    return (uint32_t)(w / 4 * 4);
+  }
+  return want ? PRE_WORDS : 0;
+}
 
 // Ladder seeds one SNV-sized haplotype strand needs (k windows) at stride D, seed length s.
 double ladder_seeds_per_strand(int k, int s, int D) {
@@ -146,9 +161,17 @@ double ladder_seeds_per_strand(int k, int s, int D) {
   return n;
 }
 
-// Modelled cost of one 2048-position warp tile: filter lookups + handling of the filter's false positives +
-// stage C work for s-mers of unrelated sequence that equal a seed by chance.
-double tile_cost(double n_entries, bool hints, int k, int s, int D, int NH, bool gf,
+// Modelled cost of one 2048-position warp tile, in cycles per scheduler: filter lookups +
+// handling of the filter's false positives + stage C for s-mers of unrelated sequence that
+// equal a seed by chance.  Constants fitted to measured scan times (profiles/README.md):
+//  * a shared-memory lookup ~16 cycles (bank-conflict wavefronts as much as its instructions);
+//  * an L2 lookup 119: an SM sustains about one random L2 load per clock, shared by its four
+//    schedulers and 32 lanes - but only while ~100 KB of L1 are left to track the loads;
+//  * behind the 128 KB pre-filter an L2 lookup costs 22 + 105 x (fraction the pre-filter passes);
+//  * a false positive 9 (strides <= 4: verified by its own lane) or 16 (macro tiles: compacted,
+//    bases re-read from L2); a chance seed match 25 (one record compare);
+//  * a seed table beyond L2 turns every probe into a DRAM access (factor `table`).
+double tile_cost(double n_entries, bool hints, int k, int s, int D, int NH, bool gf, bool pre,
                  double *seeds_out) {
   const double n_haps = n_entries / k;  // allele haplotypes (SNV-sized)
   // both strands; ref/alt haplotypes share the seeds that avoid the variant base (x0.7)
@@ -161,23 +184,14 @@ double tile_cost(double n_entries, bool hints, int k, int s, int D, int NH, bool
   const double lookups_lane = 64.0 / D, lookups_tile = 2048.0 / D;
   const double hits = lookups_tile * fp;
   const double chance = seeds / pow(4.0, s);  // P(random s-mer is a seed)
-  // Cycles per 2048-position warp tile and scheduler, fitted to measured scan times
-  // (profiles/README.md).  A shared-memory lookup is bound by bank-conflict wavefronts, not
-  // by its ~8 instructions; an L2 lookup is a fully divergent global load.  Strides <= 4:
-  // the first 32 false positives of a tile ride one pipelined probe batch, later ones wait
-  // for L2.  Strides 8, 16 (macro tiles): less fixed work per tile, but every false
-  // positive re-reads its bases from L2.  A seed table beyond L2 (32 B per seed) turns
-  // every probe into a DRAM access.
-  const double table = seeds > 2e6 ? 6.0 : seeds > 5e5 ? 1.6 : 1.0;
-  const double chance_cost = 140.0 * lookups_tile * chance;
-  if (D >= 8) {
-    const double per_lookup = gf ? L2_LOOKUP_CYCLES : 16.0 + 1.0 * NH;
-    return 160.0 + lookups_lane * per_lookup + 16.0 * table * hits + chance_cost;
-  }
-  const double per_hit = 4.4 * table;
-  const double per_lookup = gf ? L2_LOOKUP_CYCLES : 29.0 + 2.0 * NH;
-  return 136.0 + lookups_lane * per_lookup + per_hit * (hits < 32 ? hits : 32) +
-         (hits > 32 ? 2.0 * per_hit * (hits - 32) : 0.0) + chance_cost;
+  const double table = seeds > 2e6 ? 3.0 : seeds > 5e5 ? 1.3 : 1.0;
+  const double chance_cost = 25.0 * table * lookups_tile * chance;
+  double l2_lookup = 119.0;
+  if (pre) l2_lookup = 22.0 + 105.0 * (1.0 - exp(-seeds / (32.0 * pre_filter_words(true))));
+  if (D >= 8)
+    return 61.0 + lookups_lane * (gf ? l2_lookup : 16.0 + NH) + 16.0 * table * hits + chance_cost;
+  return 100.0 + lookups_lane * (gf ? l2_lookup : 13.0 + 1.5 * NH) + 9.0 * table * (hits < 64 ? hits : 64) +
+         (hits > 64 ? 14.0 * table * (hits - 64) : 0.0) + chance_cost;
 }
 
 // Resolve (s, D, NH): the caller's choice, else DKB_TUNING="s,D,NH", else the
@@ -204,8 +218,13 @@ int resolve_tuning(dkb_ctx *ctx, size_t n_entries, bool hints) {
   if (t.filter_mode < 0 || t.filter_mode > 2)
     return fail(ctx, DKB_EINVAL, "filter_mode must be 0 (auto), 1 (shared memory) or 2 (L2)");
   int best_D = 0, best_NH = 0, best_s = 0, best_gf = 0;
+  bool best_pre = false;
   double best = 1e300;
-  for (int gf = 0; gf <= 1; gf++) {
+  for (int mode = 0; mode <= 2; mode++) {  // shared memory, L2, L2 behind the pre-filter
+    const int gf = mode > 0;
+    const bool pre = mode == 2;
+    if (pre && pre_filter_words(true) == 0) continue;
+    if (mode == 1 && getenv("DKB_PREFILTER_WORDS") && pre_filter_words(true) != 0) continue;
     if (t.filter_mode && t.filter_mode != gf + 1) continue;
     for (int D = 1; D <= 16; D *= 2) {
       if (t.stride && t.stride != D) continue;
@@ -216,8 +235,8 @@ int resolve_tuning(dkb_ctx *ctx, size_t n_entries, bool hints) {
         for (int NH = 1; NH <= 4; NH++) {
           if (gf && NH > 2) continue;
           if (t.bloom_hashes ? t.bloom_hashes != NH : NH > 2) continue;  // 3, 4: manual only
-          const double c = tile_cost((double)n_entries, hints, k, s, D, NH, gf != 0, nullptr);
-          if (c < best) { best = c; best_D = D; best_NH = NH; best_s = s; best_gf = gf; }
+          const double c = tile_cost((double)n_entries, hints, k, s, D, NH, gf != 0, pre, nullptr);
+          if (c < best) { best = c; best_D = D; best_NH = NH; best_s = s; best_gf = gf; best_pre = pre; }
         }
       }
     }
@@ -230,6 +249,7 @@ int resolve_tuning(dkb_ctx *ctx, size_t n_entries, bool hints) {
   ctx->D = best_D;
   ctx->NH = best_NH;
   ctx->gf = best_gf != 0;
+  ctx->want_pre = best_pre;
   return DKB_OK;
 }
 
@@ -305,6 +325,8 @@ int launch_scan(dkb_ctx *ctx, const uint32_t *d_bases, const uint32_t *d_mask,
   P.n_tiles = (uint32_t)((n_positions + WTILE - 1) / WTILE);
   P.bloom = ctx->d_bloom;
   P.bloom_words = ctx->bloom_words;
+  P.pre = ctx->d_pre;
+  P.pre_words = ctx->gf ? ctx->pre_words : 0;
   P.st = seed_table(ctx);
   P.kt = key_table(ctx);
   P.seed_mult = SEED_MULT << (32 - 2 * ctx->s);
@@ -320,9 +342,13 @@ int launch_scan(dkb_ctx *ctx, const uint32_t *d_bases, const uint32_t *d_mask,
   if (!fn) return fail(ctx, DKB_EINVAL, "no scan kernel for this tuning");
   bool ready = false;
   for (const void *f : ctx->smem_ready) ready |= f == (const void *)fn;
-  if (!ready) {  // same carve-out in both filter modes
+  const size_t smem_bytes = ctx->gf ? SCAN_SMEM_BYTES_GF + (size_t)ctx->pre_words * 4 : SCAN_SMEM_BYTES;
+  if (!ready) {
     CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)SCAN_SMEM_BYTES));
+                            (int)smem_bytes));
+    if (ctx->gf)  // as much L1 as the lists leave
+      CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                              (int)(100 * (smem_bytes + 8192) / (228 * 1024)) + 1));
     ctx->smem_ready.push_back((const void *)fn);
   }
   // one CTA per SM; short batches get one CTA per work unit (tile, or macro tile of 4-8
@@ -341,7 +367,7 @@ int launch_scan(dkb_ctx *ctx, const uint32_t *d_bases, const uint32_t *d_mask,
     CU(cudaEventCreate(&ev.second));
   }
   CU(cudaEventRecord(ev.first, ctx->s_scan));
-  fn<<<grid, SCAN_THREADS, SCAN_SMEM_BYTES, ctx->s_scan>>>(P);
+  fn<<<grid, SCAN_THREADS, smem_bytes, ctx->s_scan>>>(P);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ev.second, ctx->s_scan));
   ctx->ev_pending.push_back(ev);
@@ -547,7 +573,7 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
       k_mark_repeats<<<g1, TB, 0, st>>>(B);
       k_apply_dead<<<g1, TB, 0, st>>>(B);
       k_assign_seeds<<<g2, TB, 0, st>>>(B, ASSIGN_COUNT, d_set, set_slots - 1, d_nseeds, SeedTable{},
-                                        nullptr, nullptr, 0, seed_mult, ctx->NH);
+                                        nullptr, nullptr, 0, nullptr, 0, seed_mult, ctx->NH);
       CU(cudaGetLastError());
     }
     unsigned int n_seeds = 0;
@@ -572,15 +598,22 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
     ctx->bloom_words = ctx->gf ? l2_filter_words((double)n_seeds) / 4 * 4 : (uint32_t)BLOOM_WORDS;
     CU(cudaMalloc(&ctx->d_bloom, (size_t)ctx->bloom_words * 4));
     CU(cudaMemsetAsync(ctx->d_bloom, 0, (size_t)ctx->bloom_words * 4, st));
+    ctx->pre_words = ctx->gf ? pre_filter_words(ctx->want_pre) : 0;
+    if (ctx->pre_words) {
+      CU(cudaMalloc(&ctx->d_pre, (size_t)ctx->pre_words * 4));
+      CU(cudaMemsetAsync(ctx->d_pre, 0, (size_t)ctx->pre_words * 4, st));
+    }
     if (n) {
       const SeedTable T = seed_table(ctx);
       k_assign_seeds<<<g2, TB, 0, st>>>(B, ASSIGN_INSERT, nullptr, 0, nullptr, T, nullptr,
-                                        ctx->d_bloom, ctx->bloom_words, seed_mult, ctx->NH);
+                                        ctx->d_bloom, ctx->bloom_words, ctx->d_pre, ctx->pre_words,
+                                        seed_mult, ctx->NH);
       k_number_seeds<<<(ctx->seed_slots + TB - 1) / TB, TB, 0, st>>>(T, ctx->seed_slots, d_nseeds);
       k_init_records<<<(uint32_t)((ns1 * 8 + TB - 1) / TB), TB, 0, st>>>(
           reinterpret_cast<uint32_t *>(ctx->d_srec), n_seeds);
       k_assign_seeds<<<g2, TB, 0, st>>>(B, ASSIGN_RECORD, nullptr, 0, nullptr, T, d_cov,
-                                        ctx->d_bloom, ctx->bloom_words, seed_mult, ctx->NH);
+                                        ctx->d_bloom, ctx->bloom_words, ctx->d_pre, ctx->pre_words,
+                                        seed_mult, ctx->NH);
       k_finish_records<<<(uint32_t)((ns1 + TB - 1) / TB), TB, 0, st>>>(
           reinterpret_cast<uint32_t *>(ctx->d_srec), d_cov, n_seeds);
       CU(cudaGetLastError());

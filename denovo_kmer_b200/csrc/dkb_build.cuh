@@ -175,8 +175,8 @@ __device__ __forceinline__ void seedset_insert(uint32_t *set, uint32_t mask, uin
 enum { ASSIGN_COUNT = 0, ASSIGN_INSERT = 1, ASSIGN_RECORD = 2 };
 __global__ void k_assign_seeds(const BuildParams B, int pass, uint32_t *set, uint32_t set_mask,
                                unsigned int *n_seeds, const SeedTable T, uint32_t *cov,
-                               uint32_t *bloom, uint32_t bloom_words, uint32_t seed_mult,
-                               int n_hashes) {
+                               uint32_t *bloom, uint32_t bloom_words, uint32_t *pre,
+                               uint32_t pre_words, uint32_t seed_mult, int n_hashes) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t i = t >> 1;
   const int ori = t & 1;
@@ -226,7 +226,11 @@ __global__ void k_assign_seeds(const BuildParams B, int pass, uint32_t *set, uin
     } else if (pass == ASSIGN_INSERT) {
       offs |= (uint32_t)(j / D) << (W * (ori * D + c));
       seedtab_insert(T, seed);
-      const uint32_t h = seed * seed_mult;
+      uint32_t h = seed * seed_mult;
+      if (pre_words) {  // one-bit pre-filter; the main filter behind it uses an independent hash
+        atomicOr(pre + bloom_word(h, pre_words), 1u << ((uint32_t)((uint64_t)h * pre_words) >> 27));
+        h *= PRE_REHASH;
+      }
       atomicOr(bloom + bloom_word(h, bloom_words), bloom_bits(seed, h, bloom_words, n_hashes));
     } else {
       const uint32_t id = T.sid[seedtab_find(T, seed)];

@@ -17,11 +17,16 @@ constexpr int WTILE_WORDS = WTILE / 16;    // 128 uint32 words of bases per warp
 constexpr int BLOOM_WORDS = 51712;         // 202 KB seed filter resident in shared memory
 constexpr int HL_CAP = 128;                // per-warp list of filter-hit ids of one tile
 constexpr int CQ_CAP = 64;                 // per-warp ring of verified seeds
-constexpr size_t SCAN_SMEM_BYTES =
-    (size_t)BLOOM_WORDS * 4 + (size_t)SCAN_WARPS * CQ_CAP * 8 + (size_t)SCAN_WARPS * HL_CAP * 2;
+constexpr size_t SCAN_LISTS_BYTES = (size_t)SCAN_WARPS * CQ_CAP * 8 + (size_t)SCAN_WARPS * HL_CAP * 2;
+constexpr size_t SCAN_SMEM_BYTES = (size_t)BLOOM_WORDS * 4 + SCAN_LISTS_BYTES;
+// L2 filter mode keeps only the lists in shared memory: the rest of the 256 KB stays L1, whose
+// lines are what outstanding global loads are tracked in (a 30 KB L1 caps an SM at ~0.3
+// random loads per clock against 1.0 with a large one: scripts/micro/l2_gather.cu).
+constexpr size_t SCAN_SMEM_BYTES_GF = SCAN_LISTS_BYTES;
 
 constexpr int MAX_SEED_LEN = 15;             // 30 bits: leaves SEED_EMPTY outside the seed space
 constexpr uint32_t SEED_MULT = 0x9E3779B1u;  // odd multiplier of the filter hash
+constexpr uint32_t PRE_REHASH = 0x85EBCA6Bu;  // odd: L2-filter hash behind a pre-filter = h * PRE_REHASH
 constexpr uint32_t SEEDTAB_MULT = 0xC2B2AE3Du; // seed bucket = (seed * SEEDTAB_MULT) >> shift
 constexpr uint32_t SEED_EMPTY = 0xFFFFFFFFu;  // free slot of the sizing set (k_assign_seeds, count_only)
 // Seed-table slot word: bits 0..29 the seed, bit 30 = slot is free, bit 31 = some seed
@@ -92,16 +97,24 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
+#ifndef DKB_NOALLOC
+#define DKB_NOALLOC 0
+#endif
+#if DKB_NOALLOC
+#define DKB_L1 ".L1::no_allocate"
+#else
+#define DKB_L1 ""
+#endif
 __device__ __forceinline__ uint4 ldg_v4_hint(const void *ptr, uint64_t pol) {
   uint4 v;
-  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+  asm volatile("ld.global.nc" DKB_L1 ".L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                : "l"(ptr), "l"(pol));
   return v;
 }
 __device__ __forceinline__ uint32_t ldg_u32_hint(const void *ptr, uint64_t pol) {
   uint32_t v;
-  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
+  asm volatile("ld.global.nc" DKB_L1 ".L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
   return v;
 }
 __device__ __forceinline__ uint64_t ldg_u64_hint(const void *ptr, uint64_t pol) {
@@ -167,6 +180,10 @@ struct ScanParams {
   const uint32_t *bloom;  // seed filter: BLOOM_WORDS words copied into shared memory per CTA,
                           // or (large candidate sets) bloom_words words probed in L2
   uint32_t bloom_words;
+  // L2 filter mode only: optional one-bit pre-filter in shared memory (pre_words words, 0 =
+  // none); only its hits go on to the L2 filter, which is then hashed with h * PRE_REHASH.
+  const uint32_t *pre;
+  uint32_t pre_words;
   SeedTable st;
   KeyTable kt;
   uint32_t seed_mult;  // SEED_MULT << (32 - 2s): the product ignores bases beyond s

@@ -5,19 +5,23 @@
 // Every stream position p with p % D == 0 has its s-mer tested against a
 // seed filter held in shared memory — or, for very large candidate tables, in
 // L2 — (stage A, the only per-position work).
-// Filter hits are compacted per warp tile and verified, 32 at a time, against
-// the exact seed table in L2 (stage B, one 16-byte bucket load per hit, issued
-// one tile ahead of its use).  A verified seed carries the offsets j at which
-// some table key designates it; each window w = p - j is rebuilt from the
-// stream, validated against the mask, canonicalised and probed in the key
-// table (stage C).  A slot is counted only when its own designated offset for
-// class (j % D) equals j, so a matching window is counted exactly once however
-// many seeds it contains (proof in DESIGN.md §4).
+// Filter hits are verified against the exact seed table in L2 with ONE 4-byte load each,
+// looked at one tile later (stage B).  At strides 2 and 4 every lane verifies its own hits
+// in up to four rounds per tile; at the other strides the hits are compacted per (macro)
+// tile and verified 32 at a time.  A verified seed has a 32-byte record: the offsets j at
+// which some table key designates it, and what those keys look like around the seed.  The
+// read is compared with that neighbourhood once; each window w = p - j inside the matching
+// run is canonicalised and probed in the key table, one window per lane (stage C).  A slot
+// is counted only when its own designated offset for class (j % D) equals j, so a matching
+// window is counted exactly once however many seeds it contains (proof in DESIGN.md §4).
 #pragma once
 #include "dkb_device.cuh"
 
 #ifndef DKB_X
-#define DKB_X 0  // timing experiments only (scripts/ab_build.sh): 1 = rounds without their load, 2 = no rounds
+// Timing experiments only, wrong counts (scripts/ab_build.sh; DESIGN.md §4 "where the time goes"):
+// 1 rounds without their load, 2 no rounds, 3-5 round loads confined to 4 B / 16 KB / 1 MB,
+// 6 no stage C, 7 stage C without its window loop.
+#define DKB_X 0
 #endif
 
 namespace dkb {
@@ -499,9 +503,23 @@ struct ScanWarp {
     unsigned long long prod;  // forced wide: ptxas would turn a plain (u64)h * n >> 32 into IMAD.HI
     uint32_t word;
     if constexpr (GF) {
-      // large candidate sets: the filter does not fit in shared memory; probe it in L2
-      asm("mul.wide.u32 %0, %1, %2;" : "=l"(prod) : "r"(h), "r"(P.bloom_words));
-      word = ldg_u32_hint(P.bloom + (uint32_t)(prod >> 32), keep);
+      // large candidate sets: the filter does not fit in shared memory; probe it in L2 -
+      // behind a one-bit shared-memory pre-filter when the build chose one (an SM sustains
+      // one random L2 load per clock at best, so every lookup the pre-filter answers counts)
+      uint32_t hh = h;
+      bool pass = true;
+      if (P.pre_words) {
+        unsigned long long p1;
+        asm("mul.wide.u32 %0, %1, %2;" : "=l"(p1) : "r"(h), "r"(P.pre_words));
+        const uint32_t addr = (uint32_t)(p1 >> 32) * P.four + fbase;
+        uint32_t w1;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(addr));
+        pass = __funnelshift_r(w1, 0, (uint32_t)p1 >> 27) & 1u;
+        hh = h * PRE_REHASH;
+      }
+      asm("mul.wide.u32 %0, %1, %2;" : "=l"(prod) : "r"(hh), "r"(P.bloom_words));
+      word = 0;
+      if (pass) word = ldg_u32_hint(P.bloom + (uint32_t)(prod >> 32), keep);
     } else {
       asm("mul.wide.u32 %0, %1, %2;" : "=l"(prod) : "r"(h), "r"(P.filter_words));
       // byte address = idx * 4 + base as a multiply-add (P.four is opaque), not an ALU-pipe LEA
@@ -575,7 +593,13 @@ __device__ __forceinline__ void load_tile(const ScanParams &P, uint32_t tile, in
                                           uint32_t (&w)[5]) {
   const uint32_t wi = tile * WTILE_WORDS + lane * 4;
   if (wi + 4 <= P.n_bwords) {
+#if DKB_NOALLOC
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(P.bases + wi), "l"(l2_policy_evict_first()));
+#else
     const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(P.bases + wi));
+#endif
     w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
   } else {
 #pragma unroll
@@ -597,12 +621,13 @@ template <int D, int NH, bool GF, bool PROF>
 __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t *filt = smem;
-  uint64_t *cq_all = reinterpret_cast<uint64_t *>(smem + BLOOM_WORDS);
+  uint64_t *cq_all = reinterpret_cast<uint64_t *>(smem + (GF ? P.pre_words : BLOOM_WORDS));
   uint16_t *hl_all = reinterpret_cast<uint16_t *>(cq_all + SCAN_WARPS * CQ_CAP);
 
-  if constexpr (!GF) {
-    for (int i = threadIdx.x; i < BLOOM_WORDS / 4; i += SCAN_THREADS)
-      reinterpret_cast<uint4 *>(filt)[i] = __ldg(reinterpret_cast<const uint4 *>(P.bloom) + i);
+  {
+    const uint32_t n4 = (GF ? P.pre_words : (uint32_t)BLOOM_WORDS) / 4;
+    const uint4 *src = reinterpret_cast<const uint4 *>(GF ? P.pre : P.bloom);
+    for (uint32_t i = threadIdx.x; i < n4; i += SCAN_THREADS) reinterpret_cast<uint4 *>(filt)[i] = __ldg(src + i);
     __syncthreads();
   }
 
