@@ -98,7 +98,7 @@ for r in csv.reader(io.StringIO(src)):
 ti = sum(v[0] for v in a2.values()) or 1
 ts = sum(v[1] for v in a2.values()) or 1
 code = open(os.path.join(ROOT, "denovo_kmer_b200", "csrc", "dkb_scan.cuh")).read().split("\n")
-PAT = r"^\s*__device__ __forceinline__ void (\w+)\(|\) (k_scan)\(const ScanParams"
+PAT = r"^\s*__device__ __forceinline__ (?:static )?[\w ]+? (\w+)\(|\) (k_scan)\(const ScanParams"
 marks = []
 for i, l in enumerate(code):
     m = re.search(PAT, l)
