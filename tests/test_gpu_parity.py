@@ -29,6 +29,30 @@ def test_snv_trio_k31(dkb, orc, tuning, hints):
     _check(dkb, orc, trio, 31, tuning=tuning, hints=hints)
 
 
+@pytest.mark.parametrize("pre_words", [0, 64, 1024, 32768])
+@pytest.mark.parametrize("tuning", [(15, 16, 2, 2), (15, 16, 1, 2), (14, 8, 2, 2), (14, 4, 2, 2), (12, 2, 1, 2)])
+def test_l2_filter_behind_prefilter(dkb, orc, tuning, pre_words, monkeypatch):
+    """L2 filter mode with the shared-memory pre-filter forced to several sizes (64 words:
+    saturated, passes nearly everything; 32768: the size the tuner uses); 0 = pure L2 mode."""
+    monkeypatch.setenv("DKB_PREFILTER_WORDS", str(pre_words))
+    trio = synth.make_trio_host(200_000, 12, 40, 31, seed=5)
+    _check(dkb, orc, trio, 31, tuning=tuning)
+    _check(dkb, orc, trio, 31, tuning=tuning, hints=False)
+
+
+def test_prefilter_chosen_by_tuner(dkb):
+    """A table of configs[1]'s size makes the tuner pick the L2 filter at stride 16 (behind the
+    pre-filter); 250 candidates keep the shared-memory filter."""
+    for n_var, want_mode in [(10_000, 2), (250, 1)]:
+        genome = synth.make_genome(max(4_000_000, n_var * 400), 1)
+        variants = synth.plant_variants(genome, n_var, 31, 2)
+        entries = dkb.variant_kmers(synth.Trio(31, genome, variants).variant_tuples(), 31)
+        with dkb.KmerCounter(31) as kc:
+            kc.build_table(entries)
+            tun = kc.tuning()
+        assert tun[1] == 16 and tun[3] == want_mode, tun
+
+
 @pytest.mark.parametrize("k", [15, 21, 25, 31, 8, 16, 30])
 def test_k_sweep(dkb, orc, k):
     trio = synth.make_trio_host(100_000, 10, 20, k, seed=7 + k)
