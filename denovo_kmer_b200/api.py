@@ -154,7 +154,8 @@ class KmerCounter:
         check(code, self._h)
 
     def set_tuning(self, seed_len=0, stride=0, bloom_hashes=0, filter_mode=0):
-        """0 = auto for every field; filter_mode 1 = shared memory, 2 = L2."""
+        """0 = auto for every field; filter_mode 1 = shared memory, 2 = L2 (with or without the
+        shared-memory pre-filter: the library's choice)."""
         t = Tuning(seed_len, stride, bloom_hashes, filter_mode)
         self._ck(self._L.dkb_ctx_set_tuning(self._h, C.byref(t)))
 
