@@ -136,7 +136,8 @@ uint32_t l2_filter_words(double seeds) {
   return (uint32_t)w;
 }
 // Shared-memory pre-filter of the L2 filter mode: 128 KB.  It must leave ~100 KB of L1, whose
-// lines track the outstanding L2 loads (192 KB of pre-filter: half the speed; profiles/README.md).
+// lines track the outstanding L2 loads.  Measured on configs[1] (Tbases/s; profiles/README.md):
+// 96 KB 4.41, 112 KB 4.50, 128 KB 4.71, 139 KB 4.16, 144 KB 4.22, 160 KB 4.38, 192 KB 2.53.
 constexpr uint32_t PRE_WORDS = 32768;
 
 // Words of the pre-filter the build should use for this table (0 = none).  DKB_PREFILTER_WORDS overrides.

@@ -97,24 +97,16 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
-#ifndef DKB_NOALLOC
-#define DKB_NOALLOC 0
-#endif
-#if DKB_NOALLOC
-#define DKB_L1 ".L1::no_allocate"
-#else
-#define DKB_L1 ""
-#endif
 __device__ __forceinline__ uint4 ldg_v4_hint(const void *ptr, uint64_t pol) {
   uint4 v;
-  asm volatile("ld.global.nc" DKB_L1 ".L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                : "l"(ptr), "l"(pol));
   return v;
 }
 __device__ __forceinline__ uint32_t ldg_u32_hint(const void *ptr, uint64_t pol) {
   uint32_t v;
-  asm volatile("ld.global.nc" DKB_L1 ".L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
   return v;
 }
 __device__ __forceinline__ uint64_t ldg_u64_hint(const void *ptr, uint64_t pol) {

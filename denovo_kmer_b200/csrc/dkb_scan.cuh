@@ -593,13 +593,7 @@ __device__ __forceinline__ void load_tile(const ScanParams &P, uint32_t tile, in
                                           uint32_t (&w)[5]) {
   const uint32_t wi = tile * WTILE_WORDS + lane * 4;
   if (wi + 4 <= P.n_bwords) {
-#if DKB_NOALLOC
-    uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(P.bases + wi), "l"(l2_policy_evict_first()));
-#else
     const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(P.bases + wi));
-#endif
     w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
   } else {
 #pragma unroll
