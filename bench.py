@@ -361,6 +361,7 @@ def run_ours(a):
                     (stream_bytes + mask_bytes) / 1e9),
                 "table_entries": int(st["n_entries"]), "seeds": int(st["n_seeds"]),
                 "tuning_seedlen_stride_hashes_filtermode": list(kc.tuning()),
+                "prefilter_words": int(st.get("prefilter_words", 0)),
                 "denovo_calls": int((calls & 1).sum()), "variants": int(len(calls)),
                 "collective": "1 NCCL allreduce(sum) of %d uint32 per step" % counts_t.numel() if world > 1 else "none",
             },

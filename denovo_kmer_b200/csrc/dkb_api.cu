@@ -854,6 +854,7 @@ int dkb_stats_get(dkb_ctx *ctx, dkb_stats *out) {
   out->scan_launches_timed = ctx->scan_launches_timed;
   out->scan_ms_total = ctx->scan_ms_total;
   out->last_scan_ms = ctx->last_scan_ms;
+  out->prefilter_words = ctx->gf ? ctx->pre_words : 0;
   return DKB_OK;
 }
 

@@ -187,6 +187,7 @@ typedef struct dkb_stats {
   uint64_t scan_launches_timed; /* launches folded into scan_ms_total */
   double scan_ms_total;      /* sum of per-launch CUDA-event times of the scan kernel */
   float last_scan_ms;        /* CUDA-event time of the most recent finished scan kernel */
+  uint32_t prefilter_words;  /* L2 filter mode: words of the shared-memory pre-filter, 0 = none */
 } dkb_stats;
 int dkb_stats_get(dkb_ctx *ctx, dkb_stats *out);
 int dkb_profile_counters(dkb_ctx *ctx, int enable);
