@@ -293,9 +293,11 @@ KeyTable key_table(const dkb_ctx *ctx) {
 typedef void (*scan_fn)(const ScanParams);
 
 scan_fn pick_scan(int D, int NH, bool gf, bool prof) {
-#ifdef DKB_AB_BUILD  // quick experimental builds (scripts/ab_build.sh): stride 4, 2 filter bits only
+#ifdef DKB_AB_BUILD  // quick experimental builds (scripts/ab_build.sh): two kernels only
   if (!gf && D == 4 && NH == 2)
     return prof ? (scan_fn)k_scan<4, 2, false, true> : (scan_fn)k_scan<4, 2, false, false>;
+  if (gf && D == 16 && NH == 2)
+    return prof ? (scan_fn)k_scan<16, 2, true, true> : (scan_fn)k_scan<16, 2, true, false>;
   return nullptr;
 #else
 #define PICKG(d, h)                                                                     \

@@ -519,7 +519,11 @@ struct ScanWarp {
       }
       asm("mul.wide.u32 %0, %1, %2;" : "=l"(prod) : "r"(hh), "r"(P.bloom_words));
       word = 0;
-      if (pass) word = ldg_u32_hint(P.bloom + (uint32_t)(prod >> 32), keep);
+      // (no L1 allocation: the filter is far larger than L1, and leaving L1 to the loads
+      // that need it is worth 4 %; the same hint on stream or table loads costs 1-2 %)
+      if (pass)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;"
+                     : "=r"(word) : "l"(P.bloom + (uint32_t)(prod >> 32)), "l"(keep));
     } else {
       asm("mul.wide.u32 %0, %1, %2;" : "=l"(prod) : "r"(h), "r"(P.filter_words));
       // byte address = idx * 4 + base as a multiply-add (P.four is opaque), not an ALU-pipe LEA
