@@ -20,7 +20,7 @@
 #ifndef DKB_X
 // Timing experiments only, wrong counts (scripts/ab_build.sh; DESIGN.md §4 "where the time goes"):
 // 1 rounds without their load, 2 no rounds, 3-5 round loads confined to 4 B / 16 KB / 1 MB,
-// 6 no stage C, 7 stage C without its window loop.
+// 6 no stage C.
 #define DKB_X 0
 #endif
 
