@@ -135,10 +135,12 @@ uint32_t l2_filter_words(double seeds) {
   if (w < BLOOM_WORDS) w = BLOOM_WORDS;
   return (uint32_t)w;
 }
-// Shared-memory pre-filter of the L2 filter mode: 128 KB.  It must leave ~100 KB of L1, whose
-// lines track the outstanding L2 loads.  Measured on configs[1] (Tbases/s; profiles/README.md):
-// 96 KB 4.41, 112 KB 4.50, 128 KB 4.71, 139 KB 4.16, 144 KB 4.22, 160 KB 4.38, 192 KB 2.53.
-constexpr uint32_t PRE_WORDS = 32768;
+// Shared-memory pre-filter of the L2 filter mode: 139 KB - with the 24 KB of lists and the
+// 1 KB the system reserves it fills the 164 KB shared-memory carve-out exactly and leaves
+// 92 KB of L1, whose lines track the outstanding L2 loads.  Measured on configs[1]
+// (Tbases/s; profiles/README.md): 107 KB (132 KB carve-out) 4.64, 128 KB 4.91, 139 KB 5.04,
+// 171 KB (196 KB carve-out, 60 KB of L1) 4.94, 192 KB 2.8.
+constexpr uint32_t PRE_WORDS = 35584;
 
 // Words of the pre-filter the build should use for this table (0 = none).  DKB_PREFILTER_WORDS overrides.
 uint32_t pre_filter_words(bool want) {
@@ -350,8 +352,10 @@ int launch_scan(dkb_ctx *ctx, const uint32_t *d_bases, const uint32_t *d_mask,
     CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)smem_bytes));
     if (ctx->gf)  // as much L1 as the lists leave
+      // the smallest carve-out that holds the block (+ 1 KB the system reserves); the hint
+      // is a percentage of 228 KB that the driver rounds UP to a supported size
       CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout,
-                              (int)(100 * (smem_bytes + 8192) / (228 * 1024)) + 1));
+                              (int)(100 * (smem_bytes + 1024) / (228 * 1024))));
     ctx->smem_ready.push_back((const void *)fn);
   }
   // one CTA per SM; short batches get one CTA per work unit (tile, or macro tile of 4-8

@@ -29,11 +29,11 @@ def test_snv_trio_k31(dkb, orc, tuning, hints):
     _check(dkb, orc, trio, 31, tuning=tuning, hints=hints)
 
 
-@pytest.mark.parametrize("pre_words", [0, 64, 1024, 32768])
+@pytest.mark.parametrize("pre_words", [0, 64, 1024, 32768, 35584])
 @pytest.mark.parametrize("tuning", [(15, 16, 2, 2), (15, 16, 1, 2), (14, 8, 2, 2), (14, 4, 2, 2), (12, 2, 1, 2)])
 def test_l2_filter_behind_prefilter(dkb, orc, tuning, pre_words, monkeypatch):
     """L2 filter mode with the shared-memory pre-filter forced to several sizes (64 words:
-    saturated, passes nearly everything; 32768: the size the tuner uses); 0 = pure L2 mode."""
+    saturated, passes nearly everything; 35584: the size the tuner uses); 0 = pure L2 mode."""
     monkeypatch.setenv("DKB_PREFILTER_WORDS", str(pre_words))
     trio = synth.make_trio_host(200_000, 12, 40, 31, seed=5)
     _check(dkb, orc, trio, 31, tuning=tuning)
