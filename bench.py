@@ -245,14 +245,22 @@ def run_ours(a):
         for p0 in range(0, n_pos, per):
             kc.submit_device(b2.data_ptr() + p0 // 4, m1.data_ptr() + p0 // 8, min(per, n_pos - p0), s)
 
-    def step():
-        kc.reset_counts()
+    # N > 1: every step's counters are summed over ranks (one NCCL allreduce) and finalised
+    # from the sum; the allreduce of step i runs on a side stream under the scans of step
+    # i + 1 and its finalise is queued behind them (dist.CountPipeline).  The timed region
+    # ends after the last step's allreduce and finalise.
+    pipe = dist.CountPipeline(kc, THRESHOLDS) if world > 1 else None
+
+    def step(last=True):
+        kc.reset_counts()  # (queued behind the previous step's copy on the scan stream)
         for s, (b2, m1, n_pos, _) in enumerate(streams):
             submit_resident(s, b2, m1, n_pos)
-        if world > 1:
-            with torch.cuda.stream(ext):
-                dist.allreduce_counts(counts_t)
-        kc.finalise_launch(THRESHOLDS)
+        if pipe is None:
+            kc.finalise_launch(THRESHOLDS)
+        else:
+            pipe.finalise(pipe.push())
+            if last:
+                pipe.flush()
 
     def barrier():
         if world > 1:
@@ -270,8 +278,8 @@ def run_ours(a):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(ext)
-    for _ in range(a.steps):
-        step()
+    for i in range(a.steps):
+        step(last=i == a.steps - 1)
     ev1.record(ext)
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -320,6 +328,9 @@ def run_ours(a):
                     n = min(pos_per_batch, n_pos - p0)
                     kc._ck(kc._L.dkb_batch_submit(kc._h, hb.data_ptr() + p0 // 4,
                                                   hm.data_ptr() + p0 // 8, n, s))
+            if world > 1:
+                with torch.cuda.stream(ext):
+                    dist.allreduce_counts(counts_t)
             return kc.finalise(THRESHOLDS)  # kernel 3 + D2H of hits/distinct/n_kmers/calls
 
         e2e_step()

@@ -64,6 +64,7 @@ SYMBOLS = {
     "dkb_entry_counts_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p),
                                           C.POINTER(C.c_size_t)]),
     "dkb_finalise": (C.c_int, [C.c_void_p, C.POINTER(Thresholds)]),
+    "dkb_finalise_from": (C.c_int, [C.c_void_p, C.POINTER(Thresholds), C.c_void_p]),
     "dkb_results_fetch": (C.c_int, [C.c_void_p, u32p, u32p, u32p, u8p]),
     "dkb_stats_get": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "dkb_profile_counters": (C.c_int, [C.c_void_p, C.c_int]),

@@ -219,10 +219,14 @@ class KmerCounter:
         self._ck(self._L.dkb_entry_counts_device(self._h, C.byref(p), C.byref(n)))
         return int(p.value or 0), int(n.value)
 
-    def finalise_launch(self, thresholds=DEFAULT_THRESHOLDS):
-        """Queue kernel 3 on the scan stream without waiting for it."""
+    def finalise_launch(self, thresholds=DEFAULT_THRESHOLDS, counts_ptr=None):
+        """Queue kernel 3 on the scan stream without waiting for it.  counts_ptr: device
+        pointer of a caller-owned copy of the [3][n_entries] counters (dkb_finalise_from)."""
         t = Thresholds(*[int(x) for x in thresholds])
-        self._ck(self._L.dkb_finalise(self._h, C.byref(t)))
+        if counts_ptr is None:
+            self._ck(self._L.dkb_finalise(self._h, C.byref(t)))
+        else:
+            self._ck(self._L.dkb_finalise_from(self._h, C.byref(t), C.c_void_p(int(counts_ptr))))
 
     def finalise(self, thresholds=DEFAULT_THRESHOLDS):
         """Kernel 3 + fetch: (hits[nv,2,3], distinct[nv,2,3], n_kmers[nv,2], calls[nv])."""

@@ -800,6 +800,12 @@ int dkb_entry_counts_device(dkb_ctx *ctx, void **d_ptr, size_t *n_u32) {
 int dkb_finalise(dkb_ctx *ctx, const dkb_thresholds *thr) {
   if (!ctx || !thr) return fail(ctx, DKB_EINVAL, "null argument");
   if (!ctx->d_counts) return fail(ctx, DKB_ESTATE, "dkb_table_build must come first");
+  return dkb_finalise_from(ctx, thr, ctx->d_counts);
+}
+
+int dkb_finalise_from(dkb_ctx *ctx, const dkb_thresholds *thr, const uint32_t *d_counts) {
+  if (!ctx || !thr || !d_counts) return fail(ctx, DKB_EINVAL, "null argument");
+  if (!ctx->d_counts) return fail(ctx, DKB_ESTATE, "dkb_table_build must come first");
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->s_scan;
   const size_t nv1 = ctx->n_variants ? ctx->n_variants : 1;
@@ -809,7 +815,7 @@ int dkb_finalise(dkb_ctx *ctx, const dkb_thresholds *thr) {
   const int TB = 256;
   if (ctx->n_entries)
     k_variant_reduce<<<(uint32_t)((ctx->n_entries + TB - 1) / TB), TB, 0, st>>>(
-        ctx->d_counts, ctx->d_variant, ctx->d_allele, ctx->d_dead, (uint32_t)ctx->n_entries,
+        d_counts, ctx->d_variant, ctx->d_allele, ctx->d_dead, (uint32_t)ctx->n_entries,
         ctx->d_hits, ctx->d_distinct, ctx->d_nkmers);
   Thresholds T{thr->min_child_alt_hits, thr->min_child_alt_distinct, thr->max_parent_alt_hits,
                thr->min_parent_ref_hits};

@@ -54,3 +54,52 @@ def allreduce_counts_numpy(counts: np.ndarray, group=None) -> np.ndarray:
     t = torch.from_numpy(counts.astype(np.int64))
     allreduce_counts(t, group)
     return t.numpy().astype(counts.dtype)
+
+
+class CountPipeline:
+    """Overlap the allreduce of one batch's counters with the scan of the next batch.
+
+    push() - call it when a batch's scans have been submitted - copies the context's counters
+    into one of two buffers on the scan stream and starts the sum over ranks on a side
+    stream; the PREVIOUS batch's reduced buffer is then finalised (kernel 3) on the scan
+    stream, behind this batch's scans, by which time its allreduce has long finished.
+    flush() finalises the last batch.  With world size 1 the allreduce is a no-op and the
+    results equal plain finalise().
+    """
+
+    def __init__(self, kc, thresholds, group=None):
+        import torch
+        self.kc, self.thr, self.group = kc, thresholds, group
+        self.dev = torch.device(f"cuda:{kc.device}")
+        self.counts = counts_tensor(kc)
+        self.bufs = [torch.empty_like(self.counts) for _ in range(2)]
+        self.scan = torch.cuda.ExternalStream(kc.scan_stream(), device=self.dev)
+        self.side = torch.cuda.Stream(device=self.dev)
+        self.copied = [torch.cuda.Event() for _ in range(2)]
+        self.reduced = [torch.cuda.Event() for _ in range(2)]
+        self.i = 0
+        self.pending = None  # buffer index whose finalise is still due
+
+    def push(self):
+        import torch
+        b = self.i & 1
+        self.i += 1
+        with torch.cuda.stream(self.scan):
+            self.bufs[b].copy_(self.counts, non_blocking=True)
+            self.copied[b].record(self.scan)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.copied[b])
+            allreduce_counts(self.bufs[b], self.group)
+            self.reduced[b].record(self.side)
+        prev, self.pending = self.pending, b
+        return prev
+
+    def finalise(self, b):
+        if b is None:
+            return
+        self.scan.wait_event(self.reduced[b])
+        self.kc.finalise_launch(self.thr, counts_ptr=self.bufs[b].data_ptr())
+
+    def flush(self):
+        b, self.pending = self.pending, None
+        self.finalise(b)

@@ -172,6 +172,11 @@ int dkb_entry_counts_device(dkb_ctx *ctx, void **d_ptr, size_t *n_u32);
 
 /* ---- kernel 3: finalise ---------------------------------------------------- */
 int dkb_finalise(dkb_ctx *ctx, const dkb_thresholds *thr);
+/* Same, from a caller-owned DEVICE copy of the counters ([DKB_N_SAMPLES][n_entries], the
+   layout of dkb_entry_counts_device) - e.g. a copy that is being summed over ranks while
+   the context's own counters already take the next batch.  Runs on the scan stream: order
+   it after the copy is complete (dkb_scan_stream). */
+int dkb_finalise_from(dkb_ctx *ctx, const dkb_thresholds *thr, const uint32_t *d_counts);
 /* hits / distinct: [n_variants][DKB_N_ALLELES][DKB_N_SAMPLES]; n_kmers:
  * [n_variants][DKB_N_ALLELES]; calls: [n_variants].  Any pointer may be NULL. */
 int dkb_results_fetch(dkb_ctx *ctx, uint32_t *hits, uint32_t *distinct, uint32_t *n_kmers,

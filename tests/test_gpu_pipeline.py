@@ -1,0 +1,56 @@
+"""-m gpu: dkb_finalise_from and the allreduce/scan overlap helper (world size 1: the sum is a no-op)."""
+import numpy as np
+import pytest
+
+from denovo_kmer_b200 import dist, synth
+from denovo_kmer_b200.api import DEFAULT_THRESHOLDS
+
+pytestmark = pytest.mark.gpu
+
+
+def _submit_all(dkb, kc, trio, k):
+    for smp in range(3):
+        seq, qual, off = trio.reads[smp]
+        kc.submit(dkb.pack_reads(seq, qual, off, 20), smp)
+
+
+def test_count_pipeline_matches_plain_finalise(dkb):
+    k = 31
+    trio = synth.make_trio_host(100_000, 10, 20, k, seed=3)
+    entries = dkb.variant_kmers(trio.variant_tuples(), k)
+    with dkb.KmerCounter(k) as kc:
+        kc.build_table(entries)
+        _submit_all(dkb, kc, trio, k)
+        plain = kc.finalise(DEFAULT_THRESHOLDS)
+        counts = kc.entry_counts().copy()
+        assert counts.sum() > 0
+        pipe = dist.CountPipeline(kc, DEFAULT_THRESHOLDS)
+        for _ in range(3):  # three batches in flight one after the other; results of the last one
+            kc.reset_counts()
+            _submit_all(dkb, kc, trio, k)
+            pipe.finalise(pipe.push())
+        pipe.flush()
+        res = kc.results()
+        for a, b in zip(plain, res):
+            assert np.array_equal(a, b)
+        assert np.array_equal(kc.entry_counts(), counts)
+
+
+def test_finalise_from_other_counts(dkb):
+    """Kernel 3 on a caller-owned copy: doubling every count doubles the hits."""
+    import torch
+    k = 21
+    trio = synth.make_trio_host(60_000, 8, 20, k, seed=4)
+    entries = dkb.variant_kmers(trio.variant_tuples(), k)
+    with dkb.KmerCounter(k) as kc:
+        kc.build_table(entries)
+        _submit_all(dkb, kc, trio, k)
+        hits, distinct, n_kmers, _ = kc.finalise(DEFAULT_THRESHOLDS)
+        t = dist.counts_tensor(kc)
+        kc.sync()
+        twice = (t * 2).contiguous()
+        torch.cuda.synchronize()
+        kc.finalise_launch(DEFAULT_THRESHOLDS, counts_ptr=twice.data_ptr())
+        hits2, distinct2, n_kmers2, _ = kc.results()
+        assert np.array_equal(hits2, hits * 2)
+        assert np.array_equal(distinct2, distinct) and np.array_equal(n_kmers2, n_kmers)
