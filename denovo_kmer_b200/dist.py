@@ -1,6 +1,7 @@
 """Multi-GPU plumbing: one process per GPU, read batches sharded across ranks, the
 spanning-k-mer table replicated, and ONE sum-allreduce of the per-entry count vector
-(north_star).  No other collective exists on the path.
+(north_star).  No other collective exists on the path.  CountPipeline overlaps
+that allreduce with the next batch's scan.
 
 The same functions run on `gloo` with CPU tensors (tests, world_size 2) and on `nccl`
 with a tensor view of the library's device counters.
