@@ -6,8 +6,8 @@
 
 One "step" = one pass of the hot path over one synthetic trio shard: counts reset, the
 three samples' packed read streams scanned (kernel 2) against the spanning-k-mer table,
-(N>1: ONE NCCL sum-allreduce of the per-entry counters), kernel 3 (per-variant reduce +
-de novo thresholds).  Default workload = BASELINE.json configs[1]: synthetic 30x trio,
+(N>1: ONE NCCL sum-allreduce of the per-entry counters, run on a side stream under the next
+step's scans), kernel 3 (per-variant reduce + de novo thresholds).  Default workload = BASELINE.json configs[1]: synthetic 30x trio,
 chr20-scale (64 Mb), 10k candidate DNMs, k=31, 150 bp reads — per GPU (weak scaling:
 every rank holds its own 64 Mb-scale shard of reads, the table is replicated).
 

@@ -123,8 +123,9 @@ class Counter {
     out.resize(3 * n_entries_);
     return out;
   }
-  Results finalise(const dkb_thresholds &t) {
-    check(dkb_finalise(ctx_, &t), ctx_);
+  // d_counts: optional caller-owned DEVICE copy of the counters (dkb_finalise_from)
+  Results finalise(const dkb_thresholds &t, const uint32_t *d_counts = nullptr) {
+    check(d_counts ? dkb_finalise_from(ctx_, &t, d_counts) : dkb_finalise(ctx_, &t), ctx_);
     Results r;
     r.hits.resize(6 * (size_t)n_variants_ + 1);
     r.distinct.resize(6 * (size_t)n_variants_ + 1);
