@@ -232,3 +232,25 @@ def test_cpp_host_layer_builds_and_refuses_without_gpu(dkb, tmp_path):
 def test_cpp_host_layer_on_gpu(dkb, tmp_path):
     out = _build_cpp_trio(tmp_path)
     assert out.returncode == 0 and out.stdout.strip() == "gpu-ok", (out.returncode, out.stdout, out.stderr)
+
+
+def test_rust_sys_crate_declares_every_symbol():
+    """bindings/rust/denovo-kmer-gpu-sys mirrors include/dkb.h (no Rust toolchain here: the
+    crate is checked textually - every exported function, every error code, the struct fields)."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "dkb.h")).read()
+    rs = open(os.path.join(root, "bindings", "rust", "denovo-kmer-gpu-sys", "src", "lib.rs")).read()
+    c_funcs = set(re.findall(r"\b(dkb_[a-z_]+)\(", hdr))
+    rs_funcs = set(re.findall(r"pub fn (dkb_[a-z_]+)\(", rs))
+    assert c_funcs == rs_funcs, (c_funcs ^ rs_funcs)
+    for name, val in re.findall(r"(DKB_E[A-Z]+|DKB_OK) = (\d+)", hdr):
+        assert re.search(rf"pub const {name}: c_int = {val};", rs), name
+    stats = re.search(r"typedef struct dkb_stats \{(.*?)\} dkb_stats;", hdr, re.S).group(1)
+    stats = re.sub(r"/\*.*?\*/", "", stats, flags=re.S)
+    c_fields = [f.strip() for decl in stats.split(";") for f in decl.split(",")]
+    c_fields = [re.sub(r"^(uint64_t|uint32_t|double|float)\s+", "", f) for f in c_fields if f.strip()]
+    rs_stats = re.search(r"pub struct DkbStats \{(.*?)\n\}", rs, re.S).group(1)
+    rs_fields = re.findall(r"pub (\w+):", rs_stats)
+    assert c_fields == rs_fields, (c_fields, rs_fields)
