@@ -30,6 +30,9 @@ pub const DKB_ECUDA: c_int = 2;
 pub const DKB_ENOMEM: c_int = 3;
 pub const DKB_ESTATE: c_int = 4;
 pub const DKB_ENODEV: c_int = 5;
+pub const DKB_ENCCL: c_int = 6;
+pub const DKB_COMM_ID_BYTES: usize = 128;
+pub const DKB_MAX_MULTI: usize = 4;
 pub const DKB_CALL_DENOVO: u8 = 0x01;
 
 extern "C" {
@@ -63,6 +66,9 @@ extern "C" {
                                   offsets: *const u64, n_reads: usize, min_baseq: c_int, sample: c_int) -> c_int;
     pub fn dkb_batch_submit_device(ctx: *mut DkbCtx, d_bases2: *const u32, d_mask1: *const u32,
                                    n_positions: u64, sample: c_int) -> c_int;
+    pub fn dkb_batch_submit_device_multi(ctx: *mut DkbCtx, n_batches: c_int, d_bases2: *const *const u32,
+                                         d_mask1: *const *const u32, n_positions: *const u64,
+                                         samples: *const c_int) -> c_int;
     pub fn dkb_sync(ctx: *mut DkbCtx) -> c_int;
     pub fn dkb_counts_reset(ctx: *mut DkbCtx) -> c_int;
     pub fn dkb_entry_counts_fetch(ctx: *mut DkbCtx, out: *mut u32) -> c_int;
@@ -71,6 +77,18 @@ extern "C" {
     pub fn dkb_finalise_from(ctx: *mut DkbCtx, thr: *const DkbThresholds, d_counts: *const u32) -> c_int;
     pub fn dkb_results_fetch(ctx: *mut DkbCtx, hits: *mut u32, distinct: *mut u32,
                              n_kmers: *mut u32, calls: *mut u8) -> c_int;
+    pub fn dkb_host_alloc(ctx: *mut DkbCtx, bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn dkb_host_free(ctx: *mut DkbCtx, p: *mut c_void) -> c_int;
+    pub fn dkb_thread_bind_near_gpu(ctx: *mut DkbCtx, numa_node_out: *mut c_int) -> c_int;
+    pub fn dkb_comm_unique_id(id_out: *mut c_void) -> c_int;
+    pub fn dkb_comm_init(ctx: *mut DkbCtx, id: *const c_void, rank: c_int, world: c_int) -> c_int;
+    pub fn dkb_comm_destroy(ctx: *mut DkbCtx) -> c_int;
+    pub fn dkb_comm_info(ctx: *const DkbCtx, rank: *mut c_int, world: *mut c_int,
+                         nccl_version: *mut c_int) -> c_int;
+    pub fn dkb_counts_allreduce(ctx: *mut DkbCtx) -> c_int;
+    pub fn dkb_reduce_push(ctx: *mut DkbCtx, thr: *const DkbThresholds) -> c_int;
+    pub fn dkb_reduce_flush(ctx: *mut DkbCtx, thr: *const DkbThresholds) -> c_int;
+    pub fn dkb_reduced_counts_fetch(ctx: *mut DkbCtx, out: *mut u32) -> c_int;
     pub fn dkb_stats_get(ctx: *mut DkbCtx, out: *mut DkbStats) -> c_int;
     pub fn dkb_profile_counters(ctx: *mut DkbCtx, enable: c_int) -> c_int;
     pub fn dkb_scan_stream(ctx: *mut DkbCtx, stream_out: *mut *mut c_void) -> c_int;

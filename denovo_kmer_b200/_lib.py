@@ -7,7 +7,9 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("DKB_LIBRARY") or os.path.join(_HERE, "libdkb.so")  # override: A/B builds
 
-OK, EINVAL, ECUDA, ENOMEM, ESTATE, ENODEV = range(6)
+OK, EINVAL, ECUDA, ENOMEM, ESTATE, ENODEV, ENCCL = range(7)
+COMM_ID_BYTES = 128
+MAX_MULTI = 4
 
 u8p = C.POINTER(C.c_uint8)
 u16p = C.POINTER(C.c_uint16)
@@ -58,6 +60,8 @@ SYMBOLS = {
                                           C.c_int]),
     "dkb_batch_submit_reads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_size_t, C.c_int, C.c_int]),
+    "dkb_batch_submit_device_multi": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p),
+                                                C.POINTER(C.c_void_p), u64p, C.POINTER(C.c_int)]),
     "dkb_sync": (C.c_int, [C.c_void_p]),
     "dkb_counts_reset": (C.c_int, [C.c_void_p]),
     "dkb_entry_counts_fetch": (C.c_int, [C.c_void_p, u32p]),
@@ -66,6 +70,18 @@ SYMBOLS = {
     "dkb_finalise": (C.c_int, [C.c_void_p, C.POINTER(Thresholds)]),
     "dkb_finalise_from": (C.c_int, [C.c_void_p, C.POINTER(Thresholds), C.c_void_p]),
     "dkb_results_fetch": (C.c_int, [C.c_void_p, u32p, u32p, u32p, u8p]),
+    "dkb_host_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "dkb_host_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dkb_thread_bind_near_gpu": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "dkb_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "dkb_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "dkb_comm_destroy": (C.c_int, [C.c_void_p]),
+    "dkb_comm_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                C.POINTER(C.c_int)]),
+    "dkb_counts_allreduce": (C.c_int, [C.c_void_p]),
+    "dkb_reduce_push": (C.c_int, [C.c_void_p, C.POINTER(Thresholds)]),
+    "dkb_reduce_flush": (C.c_int, [C.c_void_p, C.POINTER(Thresholds)]),
+    "dkb_reduced_counts_fetch": (C.c_int, [C.c_void_p, u32p]),
     "dkb_stats_get": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "dkb_profile_counters": (C.c_int, [C.c_void_p, C.c_int]),
     "dkb_scan_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

@@ -25,6 +25,13 @@ def _p(a, t):
     return a.ctypes.data_as(t) if a is not None else None
 
 
+def comm_unique_id() -> bytes:
+    """Rank 0: the 128-byte NCCL id every rank passes to KmerCounter.comm_init."""
+    buf = C.create_string_buffer(_lib.COMM_ID_BYTES)
+    check(_lib.lib().dkb_comm_unique_id(buf))
+    return buf.raw
+
+
 # ---- kmer.rs primitives -----------------------------------------------------------
 def kmer_encode(seq: str, k: int = None) -> int:
     k = len(seq) if k is None else k
@@ -136,9 +143,14 @@ class KmerCounter:
         self.n_entries = 0
         self.n_variants = 0
         self._keep = []  # host buffers of in-flight submits
+        self._pinned = []  # dkb_host_alloc blocks
 
     def close(self):
         if getattr(self, "_h", None):
+            self._L.dkb_sync(self._h)
+            for p in self._pinned:
+                self._L.dkb_host_free(self._h, p)
+            self._pinned = []
             self._L.dkb_ctx_destroy(self._h)
             self._h = None
 
@@ -199,6 +211,16 @@ class KmerCounter:
         """Device pointers (ints) of a resident stream."""
         self._ck(self._L.dkb_batch_submit_device(self._h, d_bases2, d_mask1, n_positions, sample))
 
+    def submit_device_multi(self, batches):
+        """batches: up to 4 tuples (d_bases2, d_mask1, n_positions, sample) of resident
+        streams, scanned in ONE kernel launch (e.g. the three samples of a trio)."""
+        n = len(batches)
+        b = (C.c_void_p * n)(*[int(x[0]) for x in batches])
+        m = (C.c_void_p * n)(*[int(x[1]) for x in batches])
+        npos = (C.c_uint64 * n)(*[int(x[2]) for x in batches])
+        smp = (C.c_int * n)(*[int(x[3]) for x in batches])
+        self._ck(self._L.dkb_batch_submit_device_multi(self._h, n, b, m, npos, smp))
+
     def sync(self):
         self._ck(self._L.dkb_sync(self._h))
         self._keep.clear()
@@ -241,8 +263,59 @@ class KmerCounter:
         calls = np.zeros(nv, dtype=np.uint8)
         self._ck(self._L.dkb_results_fetch(self._h, _p(hits, u32p), _p(dist, u32p), _p(nk, u32p),
                                            _p(calls, u8p)))
+        self._keep.clear()  # the fetch waited for the scan stream: every submit has been consumed
         n = self.n_variants
         return hits[:n], dist[:n], nk[:n], calls[:n]
+
+    # ---- pinned staging next to the GPU -----------------------------------------------------
+    def host_alloc(self, n_words: int) -> np.ndarray:
+        """uint32[n_words] in page-locked memory on the GPU's NUMA node (dkb_host_alloc); freed
+        when the counter is closed."""
+        p = C.c_void_p()
+        self._ck(self._L.dkb_host_alloc(self._h, max(n_words, 1) * 4, C.byref(p)))
+        self._pinned.append(p)
+        return np.ctypeslib.as_array(C.cast(p, u32p), shape=(max(n_words, 1),))[:n_words]
+
+    def bind_thread_near_gpu(self) -> int:
+        """Pin the calling thread to the CPUs of the GPU's NUMA node; returns the node (-1 unknown)."""
+        node = C.c_int(-1)
+        self._ck(self._L.dkb_thread_bind_near_gpu(self._h, C.byref(node)))
+        return node.value
+
+    # ---- multi-GPU (include/dkb.h "multi-GPU"): NCCL inside the library ------------------
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        assert len(unique_id) == _lib.COMM_ID_BYTES
+        buf = C.create_string_buffer(bytes(unique_id), _lib.COMM_ID_BYTES)
+        self._ck(self._L.dkb_comm_init(self._h, buf, rank, world))
+
+    def comm_destroy(self):
+        self._ck(self._L.dkb_comm_destroy(self._h))
+
+    def comm_info(self):
+        """(rank, communicator size as NCCL reports it, NCCL version code)"""
+        r, w, v = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._ck(self._L.dkb_comm_info(self._h, C.byref(r), C.byref(w), C.byref(v)))
+        return r.value, w.value, v.value
+
+    def counts_allreduce(self):
+        """In-place sum over ranks of the counters, on the scan stream."""
+        self._ck(self._L.dkb_counts_allreduce(self._h))
+
+    def reduce_push(self, thresholds=DEFAULT_THRESHOLDS):
+        """Snapshot the counters and start their sum over ranks on a side stream; queues
+        kernel 3 for the PREVIOUS snapshot behind the scans submitted since."""
+        t = Thresholds(*[int(x) for x in thresholds])
+        self._ck(self._L.dkb_reduce_push(self._h, C.byref(t)))
+
+    def reduce_flush(self, thresholds=DEFAULT_THRESHOLDS):
+        t = Thresholds(*[int(x) for x in thresholds])
+        self._ck(self._L.dkb_reduce_flush(self._h, C.byref(t)))
+
+    def reduced_counts(self) -> np.ndarray:
+        """Summed counters of the most recently finalised snapshot, [3, n_entries]."""
+        out = np.zeros((3, max(self.n_entries, 1)), dtype=np.uint32)
+        self._ck(self._L.dkb_reduced_counts_fetch(self._h, _p(out, u32p)))
+        return out[:, : self.n_entries]
 
     def stats(self) -> dict:
         s = Stats()

@@ -1,11 +1,18 @@
 // dkb_api.cu — the C ABI of include/dkb.h over the sm_100a kernels.
 // No CPU fallback: every compute entry point needs a CUDA device.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
+#include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <utility>
@@ -14,9 +21,9 @@
 #include "../../include/dkb.h"
 #include "dkb_build.cuh"
 #include "dkb_pack.cuh"
-#include "dkb_scan.cuh"
 
 using namespace dkb;
+static_assert(DKB_MAX_MULTI == dkb::MAX_SEGMENTS, "ABI and kernel disagree on the batches per launch");
 
 struct dkb_ctx {
   int device = 0;
@@ -40,8 +47,7 @@ struct dkb_ctx {
   uint4 *d_tslots = nullptr;
   uint32_t table_slots = 0;
   // seeds
-  uint32_t *d_seeds = nullptr, *d_sid = nullptr;
-  uint4 *d_srec = nullptr;  // seed records, 2 x uint4 per seed
+  uint4 *d_sslots = nullptr;  // seed table: 32-byte slots (seed + record), 2 x uint4 each
   uint32_t seed_slots = 0;
   uint32_t n_seeds = 0;
   uint32_t *d_bloom = nullptr, *d_pre = nullptr;
@@ -75,12 +81,26 @@ struct dkb_ctx {
   } stage[2];
   int next_stage = 0;
   uint64_t scan_launches = 0, positions_scanned = 0;
-  std::vector<const void *> smem_ready;  // scan kernels whose shared-memory limit is raised
+  // multi-GPU: the communicator and the overlapped count reduction (dkb_reduce_push)
+  void *comm = nullptr;  // ncclComm_t
+  int rank = 0, world = 1;
+  cudaStream_t s_side = nullptr;
+  uint32_t *d_red[2] = {nullptr, nullptr};  // snapshots of the counters being summed
+  size_t red_cap = 0;                       // capacity of each, in uint32
+  cudaEvent_t ev_snap[2] = {nullptr, nullptr}, ev_red[2] = {nullptr, nullptr};
+  int red_next = 0, red_pending = -1, red_last = -1;
 };
 
 namespace {
 
 thread_local std::string g_err;
+
+// Dynamic shared-memory limit and carve-out last set for each (device, scan kernel).  The
+// attributes belong to the function, not to a context, and the size an L2-filter kernel needs
+// changes with the pre-filter every table build chooses - so they are set again whenever the
+// size differs from what the function was last given, by any context of this process.
+std::mutex g_smem_mu;
+std::map<std::pair<int, const void *>, size_t> g_smem_set;
 
 int fail(dkb_ctx *ctx, int code, const std::string &msg) {
   if (ctx) ctx->err = msg;
@@ -102,12 +122,6 @@ uint32_t pow2_at_least(uint64_t x) {
   return p;
 }
 
-uint32_t log2_u32(uint32_t pow2) {
-  uint32_t l = 0;
-  while ((1u << l) < pow2) l++;
-  return l;
-}
-
 template <typename T>
 void dfree(T *&p) {
   if (p) cudaFree(p);
@@ -117,12 +131,13 @@ void dfree(T *&p) {
 void free_table(dkb_ctx *c) {
   dfree(c->d_keys); dfree(c->d_variant); dfree(c->d_allele); dfree(c->d_dead);
   dfree(c->d_tslots);
-  dfree(c->d_seeds); dfree(c->d_sid); dfree(c->d_srec); dfree(c->d_bloom); dfree(c->d_pre);
+  dfree(c->d_sslots); dfree(c->d_bloom); dfree(c->d_pre);
   dfree(c->d_counts); dfree(c->d_hits); dfree(c->d_distinct); dfree(c->d_nkmers);
   dfree(c->d_calls);
   c->n_entries = c->n_live = 0;
   c->n_variants = 0;
   c->finalised = false;
+  c->red_pending = c->red_last = -1;  // snapshots of the old table's counters are void
 }
 
 // Words of the L2-resident seed filter: 64 bits per seed, between the shared-memory size
@@ -170,7 +185,7 @@ double ladder_seeds_per_strand(int k, int s, int D) {
 //  * a shared-memory lookup ~16 cycles (bank-conflict wavefronts as much as its instructions);
 //  * an L2 lookup 119: an SM sustains about one random L2 load per clock, shared by its four
 //    schedulers and 32 lanes - but only while ~100 KB of L1 are left to track the loads;
-//  * behind the 128 KB pre-filter an L2 lookup costs 22 + 105 x (fraction the pre-filter passes);
+//  * behind the 139 KB pre-filter an L2 lookup costs 22 + 105 x (fraction the pre-filter passes);
 //  * a false positive 9 (strides <= 4: verified by its own lane) or 16 (macro tiles: compacted,
 //    bases re-read from L2); a chance seed match 25 (one record compare);
 //  * a seed table beyond L2 turns every probe into a DRAM access (factor `table`).
@@ -277,11 +292,8 @@ void collect_timing(dkb_ctx *ctx) {
 
 SeedTable seed_table(const dkb_ctx *ctx) {
   SeedTable T;
-  T.seeds = ctx->d_seeds;
-  T.sid = ctx->d_sid;
-  T.rec = ctx->d_srec;
-  T.slot_mask = ctx->seed_slots - 1;
-  T.shift = 32 - log2_u32(ctx->seed_slots);
+  T.slots = ctx->d_sslots;
+  T.n_slots = ctx->seed_slots;
   return T;
 }
 
@@ -293,41 +305,57 @@ KeyTable key_table(const dkb_ctx *ctx) {
 }
 
 typedef void (*scan_fn)(const ScanParams);
+}  // namespace
 
+// The scan kernel's instantiations are compiled one stride per translation unit
+// (dkb_scan_inst.cu with -DDKB_INST_D=...), in parallel; each exports its picker.
+namespace dkb {
+scan_fn pick_scan_d1(int NH, bool gf, bool prof);
+scan_fn pick_scan_d2(int NH, bool gf, bool prof);
+scan_fn pick_scan_d4(int NH, bool gf, bool prof);
+scan_fn pick_scan_d8(int NH, bool gf, bool prof);
+scan_fn pick_scan_d16(int NH, bool gf, bool prof);
+}  // namespace dkb
+
+namespace {
 scan_fn pick_scan(int D, int NH, bool gf, bool prof) {
-#ifdef DKB_AB_BUILD  // quick experimental builds (scripts/ab_build.sh): two kernels only
-  if (!gf && D == 4 && NH == 2)
-    return prof ? (scan_fn)k_scan<4, 2, false, true> : (scan_fn)k_scan<4, 2, false, false>;
-  if (gf && D == 16 && NH == 2)
-    return prof ? (scan_fn)k_scan<16, 2, true, true> : (scan_fn)k_scan<16, 2, true, false>;
+  switch (D) {
+    case 1: return pick_scan_d1(NH, gf, prof);
+    case 2: return pick_scan_d2(NH, gf, prof);
+    case 4: return pick_scan_d4(NH, gf, prof);
+    case 8: return pick_scan_d8(NH, gf, prof);
+    case 16: return pick_scan_d16(NH, gf, prof);
+  }
   return nullptr;
-#else
-#define PICKG(d, h)                                                                     \
-  if (gf && D == d && NH == h)                                                          \
-    return prof ? (scan_fn)k_scan<d, h, true, true> : (scan_fn)k_scan<d, h, true, false>;
-  PICKG(2, 1) PICKG(2, 2) PICKG(4, 1) PICKG(4, 2) PICKG(8, 1) PICKG(8, 2) PICKG(16, 1) PICKG(16, 2)
-#undef PICKG
-  if (gf) return nullptr;
-#define PICK(d, h)              \
-  if (D == d && NH == h)        \
-    return prof ? (scan_fn)k_scan<d, h, false, true> : (scan_fn)k_scan<d, h, false, false>;
-  PICK(1, 1) PICK(1, 2) PICK(1, 3) PICK(1, 4) PICK(2, 1) PICK(2, 2) PICK(2, 3) PICK(2, 4)
-  PICK(4, 1) PICK(4, 2) PICK(4, 3) PICK(4, 4) PICK(8, 1) PICK(8, 2) PICK(8, 3) PICK(8, 4)
-  PICK(16, 1) PICK(16, 2) PICK(16, 3) PICK(16, 4)
-#undef PICK
-  return nullptr;
-#endif
 }
 
-int launch_scan(dkb_ctx *ctx, const uint32_t *d_bases, const uint32_t *d_mask,
-                uint64_t n_positions, int sample) {
+// One scan launch over n_seg device-resident packed streams (each into its sample's counters).
+int launch_scan(dkb_ctx *ctx, int n_seg, const uint32_t *const *d_bases, const uint32_t *const *d_mask,
+                const uint64_t *n_positions, const int *samples) {
   ScanParams P;
-  P.bases = d_bases;
-  P.mask = d_mask;
-  P.n_pos = (uint32_t)n_positions;
-  P.n_bwords = (uint32_t)dkb_stream_bases_words(n_positions);
-  P.n_mwords = (uint32_t)dkb_stream_mask_words(n_positions);
-  P.n_tiles = (uint32_t)((n_positions + WTILE - 1) / WTILE);
+  memset(&P, 0, sizeof(P));
+  // work units: tiles, or macro tiles of 4-8 tiles at strides 8/16
+  const uint32_t per_unit = ctx->D >= 8 ? 32u / (64u / ctx->D) : 1u;
+  uint64_t units = 0, total_pos = 0;
+  P.n_seg = 0;
+  for (int i = 0; i < n_seg; i++) {
+    if (n_positions[i] == 0) continue;
+    ScanSegment &S = P.seg[P.n_seg++];
+    S.bases = d_bases[i];
+    S.mask = d_mask[i];
+    S.counts = ctx->d_counts + (size_t)samples[i] * ctx->n_entries;
+    S.n_pos = (uint32_t)n_positions[i];
+    S.n_bwords = (uint32_t)dkb_stream_bases_words(n_positions[i]);
+    S.n_mwords = (uint32_t)dkb_stream_mask_words(n_positions[i]);
+    S.n_tiles = (uint32_t)((n_positions[i] + WTILE - 1) / WTILE);
+    S.unit_begin = (uint32_t)units;
+    units += (S.n_tiles + per_unit - 1) / per_unit;
+    S.unit_end = (uint32_t)units;
+    total_pos += n_positions[i];
+  }
+  if (P.n_seg == 0) return DKB_OK;
+  if (units >= 0xFFFF0000ull) return fail(ctx, DKB_EINVAL, "too many positions in one launch");
+  for (int i = P.n_seg; i < MAX_SEGMENTS; i++) P.seg[i] = P.seg[P.n_seg - 1];  // never indexed; keep valid
   P.bloom = ctx->d_bloom;
   P.bloom_words = ctx->bloom_words;
   P.pre = ctx->d_pre;
@@ -339,31 +367,30 @@ int launch_scan(dkb_ctx *ctx, const uint32_t *d_bases, const uint32_t *d_mask,
   P.four = 4;
   for (int i = 0; i < 32; i++) P.pw[i] = 1u << i;
   P.filter_words = BLOOM_WORDS;
-  P.counts = ctx->d_counts + (size_t)sample * ctx->n_entries;
   P.k = ctx->k;
   P.s = ctx->s;
   P.prof = ctx->d_prof;
   scan_fn fn = pick_scan(ctx->D, ctx->NH, ctx->gf, ctx->prof);
   if (!fn) return fail(ctx, DKB_EINVAL, "no scan kernel for this tuning");
-  bool ready = false;
-  for (const void *f : ctx->smem_ready) ready |= f == (const void *)fn;
   const size_t smem_bytes = ctx->gf ? SCAN_SMEM_BYTES_GF + (size_t)ctx->pre_words * 4 : SCAN_SMEM_BYTES;
-  if (!ready) {
-    CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)smem_bytes));
-    if (ctx->gf)  // as much L1 as the lists leave
-      // the smallest carve-out that holds the block (+ 1 KB the system reserves); the hint
-      // is a percentage of 228 KB that the driver rounds UP to a supported size
+  {
+    std::lock_guard<std::mutex> lk(g_smem_mu);
+    auto it = g_smem_set.find({ctx->device, (const void *)fn});
+    if (it == g_smem_set.end() || it->second != smem_bytes) {
+      CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)smem_bytes));
+      // L2 filter mode: as much L1 as the block leaves - the smallest carve-out that holds it
+      // (+ 1 KB the system reserves); the hint is a percentage of 228 KB that the driver rounds
+      // UP to a supported size.  Shared-memory filter mode: everything.
       CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributePreferredSharedMemoryCarveout,
-                              (int)(100 * (smem_bytes + 1024) / (228 * 1024))));
-    ctx->smem_ready.push_back((const void *)fn);
+                              ctx->gf ? (int)(100 * (smem_bytes + 1024) / (228 * 1024))
+                                      : (int)cudaSharedmemCarveoutMaxShared));
+      g_smem_set[{ctx->device, (const void *)fn}] = smem_bytes;
+    }
   }
-  // one CTA per SM; short batches get one CTA per work unit (tile, or macro tile of 4-8
-  // tiles at strides 8/16) so that they still spread over the SMs
-  const uint32_t per_unit = ctx->D >= 8 ? 32u / (64u / ctx->D) : 1u;
-  uint32_t grid = (P.n_tiles + per_unit - 1) / per_unit;
+  // one CTA per SM; short batches get one CTA per work unit so that they still spread over the SMs
+  uint32_t grid = (uint32_t)units;
   if (grid > (uint32_t)ctx->n_sms) grid = ctx->n_sms;
-  if (grid == 0) return DKB_OK;
   if (ctx->ev_pending.size() >= 256) collect_timing(ctx);
   std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
   if (!ctx->ev_pool.empty()) {
@@ -379,9 +406,14 @@ int launch_scan(dkb_ctx *ctx, const uint32_t *d_bases, const uint32_t *d_mask,
   CU(cudaEventRecord(ev.second, ctx->s_scan));
   ctx->ev_pending.push_back(ev);
   ctx->scan_launches++;
-  ctx->positions_scanned += n_positions;
+  ctx->positions_scanned += total_pos;
   ctx->finalised = false;
   return DKB_OK;
+}
+
+int launch_scan(dkb_ctx *ctx, const uint32_t *d_bases, const uint32_t *d_mask, uint64_t n_positions,
+                int sample) {
+  return launch_scan(ctx, 1, &d_bases, &d_mask, &n_positions, &sample);
 }
 
 // Grow a staging buffer (elements of T); the caller has made sure no kernel still reads it.
@@ -389,9 +421,156 @@ template <typename T>
 int grow(dkb_ctx *ctx, T *&p, size_t &cap, size_t need) {
   if (cap >= need) return DKB_OK;
   dfree(p);
-  cap = need + need / 8 + 256;
-  CU(cudaMalloc(&p, cap * sizeof(T)));
+  cap = 0;  // a failed allocation must not leave a capacity behind a null pointer
+  const size_t want = need + need / 8 + 256;
+  T *q = nullptr;
+  CU(cudaMalloc(&q, want * sizeof(T)));
+  p = q;
+  cap = want;
   return DKB_OK;
+}
+
+// ---- host memory next to the GPU ---------------------------------------------------------
+// NUMA node of the device's PCIe slot (-1 if the system does not say) and that node's CPUs.
+int gpu_numa_node(int device) {
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  for (char *c = bus; *c; c++) *c = (char)tolower(*c);
+  std::ifstream f(std::string("/sys/bus/pci/devices/") + bus + "/numa_node");
+  int node = -1;
+  if (!(f >> node)) return -1;
+  return node;
+}
+
+bool node_cpus(int node, cpu_set_t *set) {
+  std::ifstream f("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist");
+  std::string list;
+  if (!std::getline(f, list)) return false;
+  CPU_ZERO(set);
+  int n = 0;
+  size_t i = 0;
+  while (i < list.size()) {  // "0-31,64-95"
+    char *end = nullptr;
+    long a = strtol(list.c_str() + i, &end, 10), b = a;
+    if (end == list.c_str() + i) break;
+    i = end - list.c_str();
+    if (i < list.size() && list[i] == '-') {
+      b = strtol(list.c_str() + i + 1, &end, 10);
+      i = end - list.c_str();
+    }
+    for (long c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET((int)c, set); n++; }
+    if (i < list.size() && list[i] == ',') i++;
+  }
+  return n > 0;
+}
+
+// Prefer `node` for this thread's page allocations (-1: back to the default policy).  Best
+// effort: containers often forbid the call, and then CPU affinity + first touch decide.
+void prefer_node(int node) {
+#ifdef SYS_set_mempolicy
+  if (node < 0) {
+    syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0);
+    return;
+  }
+  unsigned long mask[16] = {0};
+  if (node >= (int)(sizeof(mask) * 8)) return;
+  mask[node / (8 * sizeof(long))] |= 1ul << (node % (8 * sizeof(long)));
+  syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, sizeof(mask) * 8);
+#else
+  (void)node;
+#endif
+}
+
+// ---- NCCL, bound at run time ---------------------------------------------------------
+// libnccl.so.2 is opened with dlopen the first time a communicator is asked for, so a
+// single-GPU user needs no NCCL at all; in a process that already holds NCCL (PyTorch's
+// bundled copy) the same library instance is used.  Only the calls below are needed; their
+// C signatures are stable across NCCL 2.x.
+struct NcclId { char internal[128]; };  // ncclUniqueId
+struct Nccl {
+  void *h = nullptr;
+  int (*GetUniqueId)(NcclId *) = nullptr;
+  int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  int (*CommCount)(void *, int *) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  int (*GetVersion)(int *) = nullptr;
+  std::string err;
+};
+constexpr int NCCL_UINT32 = 3, NCCL_SUM = 0;  // ncclUint32, ncclSum
+
+Nccl *nccl() {
+  static Nccl N;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char *names[] = {getenv("DKB_NCCL_LIBRARY"), "libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+      if (!nm || !*nm) continue;
+      if ((N.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL))) break;
+      N.err = dlerror();
+    }
+    if (!N.h) return;
+    auto sym = [&](const char *name) {
+      void *p = dlsym(N.h, name);
+      if (!p) N.err = std::string("missing NCCL symbol ") + name;
+      return p;
+    };
+    N.GetUniqueId = (decltype(N.GetUniqueId))sym("ncclGetUniqueId");
+    N.CommInitRank = (decltype(N.CommInitRank))sym("ncclCommInitRank");
+    N.CommDestroy = (decltype(N.CommDestroy))sym("ncclCommDestroy");
+    N.CommCount = (decltype(N.CommCount))sym("ncclCommCount");
+    N.AllReduce = (decltype(N.AllReduce))sym("ncclAllReduce");
+    N.GetErrorString = (decltype(N.GetErrorString))sym("ncclGetErrorString");
+    N.GetVersion = (decltype(N.GetVersion))sym("ncclGetVersion");
+    if (!N.GetUniqueId || !N.CommInitRank || !N.CommDestroy || !N.AllReduce || !N.GetErrorString) {
+      dlclose(N.h);
+      N.h = nullptr;
+    }
+  });
+  return &N;
+}
+
+#define NC(call)                                                                              \
+  do {                                                                                        \
+    int r_ = (call);                                                                          \
+    if (r_ != 0)                                                                              \
+      return fail(ctx, DKB_ENCCL, std::string(#call) + ": " + nccl()->GetErrorString(r_));    \
+  } while (0)
+
+// Side stream, events and the two snapshot buffers of the overlapped reduction.
+int reduce_setup(dkb_ctx *ctx) {
+  const size_t need = (ctx->n_entries ? ctx->n_entries : 1) * 3;
+  if (!ctx->s_side) {
+    CU(cudaStreamCreateWithFlags(&ctx->s_side, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      CU(cudaEventCreateWithFlags(&ctx->ev_snap[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&ctx->ev_red[i], cudaEventDisableTiming));
+    }
+  }
+  if (ctx->red_cap < need) {
+    CU(cudaStreamSynchronize(ctx->s_side));
+    CU(cudaStreamSynchronize(ctx->s_scan));
+    for (int i = 0; i < 2; i++) dfree(ctx->d_red[i]);
+    ctx->red_cap = 0;
+    for (int i = 0; i < 2; i++) CU(cudaMalloc(&ctx->d_red[i], need * 4));
+    ctx->red_cap = need;
+    ctx->red_pending = ctx->red_last = -1;
+  }
+  return DKB_OK;
+}
+
+int finalise_counts(dkb_ctx *ctx, const dkb_thresholds *thr, const uint32_t *d_counts);
+
+// Kernel 3 on snapshot b, on the scan stream, once its sum over ranks is complete.
+int finalise_snapshot(dkb_ctx *ctx, const dkb_thresholds *thr, int b) {
+  CU(cudaStreamWaitEvent(ctx->s_scan, ctx->ev_red[b], 0));
+  int rc = finalise_counts(ctx, thr, ctx->d_red[b]);
+  ctx->red_last = b;
+  return rc;
 }
 
 }  // namespace
@@ -408,6 +587,7 @@ const char *dkb_strerror(int code) {
     case DKB_ENOMEM: return "out of memory";
     case DKB_ESTATE: return "call out of order";
     case DKB_ENODEV: return "no usable CUDA device (no CPU fallback exists)";
+    case DKB_ENCCL: return "NCCL error";
     default: return "unknown error";
   }
 }
@@ -479,6 +659,13 @@ int dkb_ctx_destroy(dkb_ctx *ctx) {
       cudaEventDestroy(pr.first);
       cudaEventDestroy(pr.second);
     }
+  if (ctx->comm && nccl()->h) nccl()->CommDestroy(ctx->comm);
+  for (int i = 0; i < 2; i++) {
+    dfree(ctx->d_red[i]);
+    if (ctx->ev_snap[i]) cudaEventDestroy(ctx->ev_snap[i]);
+    if (ctx->ev_red[i]) cudaEventDestroy(ctx->ev_red[i]);
+  }
+  if (ctx->s_side) cudaStreamDestroy(ctx->s_side);
   if (ctx->s_scan) cudaStreamDestroy(ctx->s_scan);
   if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
   delete ctx;
@@ -533,8 +720,11 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
   uint32_t *d_slot_of = nullptr;
   uint32_t *d_set = nullptr, *d_cov = nullptr;
   unsigned int *d_nseeds = nullptr;
+  unsigned long long *d_stats = nullptr;
   cudaStream_t st = ctx->s_scan;
-  auto cleanup = [&]() { dfree(d_wi); dfree(d_wc); dfree(d_slot_of); dfree(d_set); dfree(d_cov); dfree(d_nseeds); };
+  auto cleanup = [&]() {
+    dfree(d_wi); dfree(d_wc); dfree(d_slot_of); dfree(d_set); dfree(d_cov); dfree(d_nseeds); dfree(d_stats);
+  };
   rc = [&]() -> int {
     CU(cudaMalloc(&ctx->d_keys, n1 * 8));
     CU(cudaMalloc(&ctx->d_variant, n1 * 4));
@@ -587,21 +777,17 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
     CU(cudaMemcpyAsync(&n_seeds, d_nseeds, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     ctx->n_seeds = n_seeds;
-    // At most 1/8 full: a filter false positive lands on a slot marked ST_MOVED_BIT (second
-    // load) about once in a hundred probes; 16 slots per seed halve that but cost more L2
-    // (measured 2-7 % slower at every stride).
-    int per_seed = 8;
-    if (const char *e = getenv("DKB_SEED_SLOTS_PER_SEED")) per_seed = atoi(e) > 1 ? atoi(e) : per_seed;
-    ctx->seed_slots = pow2_at_least((uint64_t)per_seed * n_seeds + 2);
-    CU(cudaMalloc(&ctx->d_seeds, (size_t)ctx->seed_slots * 4));
-    CU(cudaMalloc(&ctx->d_sid, (size_t)ctx->seed_slots * 4));
-    const size_t ns1 = n_seeds ? n_seeds : 1;
-    CU(cudaMalloc(&ctx->d_srec, ns1 * 32));
-    CU(cudaMalloc(&d_cov, ns1 * 12));
-    CU(cudaMemsetAsync(d_cov, 0, ns1 * 12, st));
-    CU(cudaMemsetAsync(d_nseeds, 0, 4, st));  // reused as the numbering counter
-    CU(cudaMemsetAsync(ctx->d_seeds, 0x40, (size_t)ctx->seed_slots * 4, st));  // ST_EMPTY
-    CU(cudaMemsetAsync(ctx->d_sid, 0, (size_t)ctx->seed_slots * 4, st));
+    // Seed table: 32-byte slots (seed + record), half full, any size.  Only occupied slots are
+    // ever touched by true hits, so the hot set is 32 B per seed; an absent seed (a filter
+    // false positive) lands on a slot marked ST_MOVED_BIT - a second load - about one time in 8.
+    double per_seed = 2.0;
+    if (const char *e = getenv("DKB_SEED_SLOTS_PER_SEED")) per_seed = atof(e) >= 1.1 ? atof(e) : per_seed;
+    const double want_slots = per_seed * n_seeds + 64;
+    if (want_slots >= 4294967295.0) return fail(ctx, DKB_EINVAL, "too many seeds for the seed table");
+    ctx->seed_slots = (uint32_t)want_slots;
+    CU(cudaMalloc(&ctx->d_sslots, (size_t)ctx->seed_slots * 32));
+    CU(cudaMalloc(&d_cov, (size_t)ctx->seed_slots * 12));
+    CU(cudaMemsetAsync(d_cov, 0, (size_t)ctx->seed_slots * 12, st));
     ctx->bloom_words = ctx->gf ? l2_filter_words((double)n_seeds) / 4 * 4 : (uint32_t)BLOOM_WORDS;
     CU(cudaMalloc(&ctx->d_bloom, (size_t)ctx->bloom_words * 4));
     CU(cudaMemsetAsync(ctx->d_bloom, 0, (size_t)ctx->bloom_words * 4, st));
@@ -610,30 +796,27 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
       CU(cudaMalloc(&ctx->d_pre, (size_t)ctx->pre_words * 4));
       CU(cudaMemsetAsync(ctx->d_pre, 0, (size_t)ctx->pre_words * 4, st));
     }
+    const SeedTable T = seed_table(ctx);
+    k_init_slots<<<(uint32_t)((2 * (size_t)ctx->seed_slots + TB - 1) / TB), TB, 0, st>>>(T);
     if (n) {
-      const SeedTable T = seed_table(ctx);
       k_assign_seeds<<<g2, TB, 0, st>>>(B, ASSIGN_INSERT, nullptr, 0, nullptr, T, nullptr,
                                         ctx->d_bloom, ctx->bloom_words, ctx->d_pre, ctx->pre_words,
                                         seed_mult, ctx->NH);
-      k_number_seeds<<<(ctx->seed_slots + TB - 1) / TB, TB, 0, st>>>(T, ctx->seed_slots, d_nseeds);
-      k_init_records<<<(uint32_t)((ns1 * 8 + TB - 1) / TB), TB, 0, st>>>(
-          reinterpret_cast<uint32_t *>(ctx->d_srec), n_seeds);
       k_assign_seeds<<<g2, TB, 0, st>>>(B, ASSIGN_RECORD, nullptr, 0, nullptr, T, d_cov,
                                         ctx->d_bloom, ctx->bloom_words, ctx->d_pre, ctx->pre_words,
                                         seed_mult, ctx->NH);
-      k_finish_records<<<(uint32_t)((ns1 + TB - 1) / TB), TB, 0, st>>>(
-          reinterpret_cast<uint32_t *>(ctx->d_srec), d_cov, n_seeds);
-      CU(cudaGetLastError());
+      k_finish_records<<<(ctx->seed_slots + TB - 1) / TB, TB, 0, st>>>(T, d_cov);
     }
-    std::vector<uint32_t> bloom(ctx->bloom_words);
-    std::vector<uint8_t> dead(n1);
-    CU(cudaMemcpyAsync(bloom.data(), ctx->d_bloom, (size_t)ctx->bloom_words * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(dead.data(), ctx->d_dead, n1, cudaMemcpyDeviceToHost, st));
+    // build statistics, counted on the device (the filter can be 16 MB)
+    CU(cudaMalloc(&d_stats, 16));
+    CU(cudaMemsetAsync(d_stats, 0, 16, st));
+    k_build_stats<<<296, 256, 0, st>>>(ctx->d_bloom, ctx->bloom_words, ctx->d_dead, (uint32_t)n, d_stats);
+    CU(cudaGetLastError());
+    unsigned long long h_stats[2] = {0, 0};
+    CU(cudaMemcpyAsync(h_stats, d_stats, 16, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    ctx->bloom_bits_set = 0;
-    for (uint32_t w : bloom) ctx->bloom_bits_set += (uint64_t)__builtin_popcount(w);
-    ctx->n_live = 0;
-    for (size_t i = 0; i < n; i++) ctx->n_live += !dead[i];
+    ctx->bloom_bits_set = h_stats[0];
+    ctx->n_live = (size_t)h_stats[1];
     return DKB_OK;
   }();
   cleanup();
@@ -649,10 +832,29 @@ int dkb_batch_submit_device(dkb_ctx *ctx, const uint32_t *d_bases2, const uint32
   if (n_positions == 0) return DKB_OK;
   if (n_positions > 0xFFFFF000ull) return fail(ctx, DKB_EINVAL, "batch too long (max 2^32 - 4096 positions)");
   if (!d_bases2 || !d_mask1) return fail(ctx, DKB_EINVAL, "null stream pointer");
-  if (((uintptr_t)d_bases2 & 15) || ((uintptr_t)d_mask1 & 3))
-    return fail(ctx, DKB_EINVAL, "bases2 must be 16-byte aligned");
+  if ((uintptr_t)d_bases2 & 15) return fail(ctx, DKB_EINVAL, "d_bases2 must be 16-byte aligned");
+  if ((uintptr_t)d_mask1 & 3) return fail(ctx, DKB_EINVAL, "d_mask1 must be 4-byte aligned");
   CU(cudaSetDevice(ctx->device));
   return launch_scan(ctx, d_bases2, d_mask1, n_positions, sample);
+}
+
+int dkb_batch_submit_device_multi(dkb_ctx *ctx, int n_batches, const uint32_t *const *d_bases2,
+                                  const uint32_t *const *d_mask1, const uint64_t *n_positions,
+                                  const int *samples) {
+  if (!ctx) return fail(nullptr, DKB_EINVAL, "ctx is null");
+  if (!ctx->d_tslots) return fail(ctx, DKB_ESTATE, "dkb_table_build must come first");
+  if (n_batches < 0 || n_batches > DKB_MAX_MULTI) return fail(ctx, DKB_EINVAL, "n_batches out of range");
+  if (n_batches && (!d_bases2 || !d_mask1 || !n_positions || !samples)) return fail(ctx, DKB_EINVAL, "null argument");
+  for (int i = 0; i < n_batches; i++) {
+    if (samples[i] < 0 || samples[i] >= DKB_N_SAMPLES) return fail(ctx, DKB_EINVAL, "sample must be 0, 1 or 2");
+    if (n_positions[i] == 0) continue;
+    if (n_positions[i] > 0xFFFFF000ull) return fail(ctx, DKB_EINVAL, "batch too long (max 2^32 - 4096 positions)");
+    if (!d_bases2[i] || !d_mask1[i]) return fail(ctx, DKB_EINVAL, "null stream pointer");
+    if ((uintptr_t)d_bases2[i] & 15) return fail(ctx, DKB_EINVAL, "d_bases2 must be 16-byte aligned");
+    if ((uintptr_t)d_mask1[i] & 3) return fail(ctx, DKB_EINVAL, "d_mask1 must be 4-byte aligned");
+  }
+  CU(cudaSetDevice(ctx->device));
+  return launch_scan(ctx, n_batches, d_bases2, d_mask1, n_positions, samples);
 }
 
 int dkb_batch_submit(dkb_ctx *ctx, const uint32_t *bases2, const uint32_t *mask1,
@@ -671,12 +873,9 @@ int dkb_batch_submit(dkb_ctx *ctx, const uint32_t *bases2, const uint32_t *mask1
   if (st.bases_cap < bw || st.mask_cap < mw) {
     // the previous scan may still read the old buffers
     if (st.in_use) CU(cudaEventSynchronize(st.freed));
-    dfree(st.bases);
-    dfree(st.mask);
-    st.bases_cap = bw + bw / 8 + 64;
-    st.mask_cap = mw + mw / 8 + 64;
-    CU(cudaMalloc(&st.bases, st.bases_cap * 4));
-    CU(cudaMalloc(&st.mask, st.mask_cap * 4));
+    int rc;
+    if ((rc = grow(ctx, st.bases, st.bases_cap, bw)) != DKB_OK) return rc;
+    if ((rc = grow(ctx, st.mask, st.mask_cap, mw)) != DKB_OK) return rc;
   }
   CU(cudaMemcpyAsync(st.bases, bases2, bw * 4, cudaMemcpyHostToDevice, ctx->s_copy));
   CU(cudaMemcpyAsync(st.mask, mask1, mw * 4, cudaMemcpyHostToDevice, ctx->s_copy));
@@ -807,6 +1006,13 @@ int dkb_finalise_from(dkb_ctx *ctx, const dkb_thresholds *thr, const uint32_t *d
   if (!ctx || !thr || !d_counts) return fail(ctx, DKB_EINVAL, "null argument");
   if (!ctx->d_counts) return fail(ctx, DKB_ESTATE, "dkb_table_build must come first");
   CU(cudaSetDevice(ctx->device));
+  return finalise_counts(ctx, thr, d_counts);
+}
+
+}  // extern "C"
+
+namespace {
+int finalise_counts(dkb_ctx *ctx, const dkb_thresholds *thr, const uint32_t *d_counts) {
   cudaStream_t st = ctx->s_scan;
   const size_t nv1 = ctx->n_variants ? ctx->n_variants : 1;
   CU(cudaMemsetAsync(ctx->d_hits, 0, nv1 * 6 * 4, st));
@@ -824,6 +1030,116 @@ int dkb_finalise_from(dkb_ctx *ctx, const dkb_thresholds *thr, const uint32_t *d
                                                             ctx->n_variants, T, ctx->d_calls);
   CU(cudaGetLastError());
   ctx->finalised = true;
+  return DKB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+// ---- multi-GPU: one sum over ranks of the per-entry counters ---------------------------
+int dkb_comm_unique_id(void *id_out) {
+  dkb_ctx *ctx = nullptr;
+  if (!id_out) return fail(nullptr, DKB_EINVAL, "id_out is null");
+  if (!nccl()->h) return fail(nullptr, DKB_ENCCL, "cannot load libnccl.so.2: " + nccl()->err);
+  NcclId id;
+  NC(nccl()->GetUniqueId(&id));
+  memcpy(id_out, &id, sizeof(id));
+  return DKB_OK;
+}
+
+int dkb_comm_init(dkb_ctx *ctx, const void *id, int rank, int world) {
+  if (!ctx || !id) return fail(ctx, DKB_EINVAL, "null argument");
+  if (world < 1 || rank < 0 || rank >= world) return fail(ctx, DKB_EINVAL, "rank / world out of range");
+  if (ctx->comm) return fail(ctx, DKB_ESTATE, "communicator already initialised");
+  if (!nccl()->h) return fail(ctx, DKB_ENCCL, "cannot load libnccl.so.2: " + nccl()->err);
+  CU(cudaSetDevice(ctx->device));
+  NcclId nid;
+  memcpy(&nid, id, sizeof(nid));
+  void *comm = nullptr;
+  NC(nccl()->CommInitRank(&comm, world, nid, rank));
+  ctx->comm = comm;
+  ctx->rank = rank;
+  ctx->world = world;
+  return DKB_OK;
+}
+
+int dkb_comm_destroy(dkb_ctx *ctx) {
+  if (!ctx) return fail(nullptr, DKB_EINVAL, "ctx is null");
+  if (!ctx->comm) return DKB_OK;
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->s_side) CU(cudaStreamSynchronize(ctx->s_side));
+  CU(cudaStreamSynchronize(ctx->s_scan));
+  NC(nccl()->CommDestroy(ctx->comm));
+  ctx->comm = nullptr;
+  ctx->rank = 0;
+  ctx->world = 1;
+  return DKB_OK;
+}
+
+int dkb_comm_info(const dkb_ctx *ctx_c, int *rank, int *world, int *nccl_version) {
+  dkb_ctx *ctx = const_cast<dkb_ctx *>(ctx_c);
+  if (!ctx) return fail(nullptr, DKB_EINVAL, "ctx is null");
+  if (rank) *rank = ctx->rank;
+  if (world) *world = ctx->world;
+  if (world && ctx->comm && nccl()->CommCount) NC(nccl()->CommCount(ctx->comm, world));
+  if (nccl_version) {
+    *nccl_version = 0;
+    if (ctx->comm && nccl()->GetVersion) nccl()->GetVersion(nccl_version);
+  }
+  return DKB_OK;
+}
+
+int dkb_counts_allreduce(dkb_ctx *ctx) {
+  if (!ctx) return fail(nullptr, DKB_EINVAL, "ctx is null");
+  if (!ctx->d_counts) return fail(ctx, DKB_ESTATE, "dkb_table_build must come first");
+  if (!ctx->comm || ctx->world == 1) return DKB_OK;
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->n_entries)
+    NC(nccl()->AllReduce(ctx->d_counts, ctx->d_counts, ctx->n_entries * 3, NCCL_UINT32, NCCL_SUM,
+                         ctx->comm, ctx->s_scan));
+  ctx->finalised = false;
+  return DKB_OK;
+}
+
+int dkb_reduce_push(dkb_ctx *ctx, const dkb_thresholds *thr) {
+  if (!ctx || !thr) return fail(ctx, DKB_EINVAL, "null argument");
+  if (!ctx->d_counts) return fail(ctx, DKB_ESTATE, "dkb_table_build must come first");
+  CU(cudaSetDevice(ctx->device));
+  int rc = reduce_setup(ctx);
+  if (rc != DKB_OK) return rc;
+  const int b = ctx->red_next;
+  ctx->red_next ^= 1;
+  const size_t n = ctx->n_entries * 3;
+  // snapshot on the scan stream (behind this batch's scans) ...
+  if (n) CU(cudaMemcpyAsync(ctx->d_red[b], ctx->d_counts, n * 4, cudaMemcpyDeviceToDevice, ctx->s_scan));
+  CU(cudaEventRecord(ctx->ev_snap[b], ctx->s_scan));
+  // ... summed over ranks on the side stream while the scan stream moves on
+  CU(cudaStreamWaitEvent(ctx->s_side, ctx->ev_snap[b], 0));
+  if (ctx->comm && ctx->world > 1 && n)
+    NC(nccl()->AllReduce(ctx->d_red[b], ctx->d_red[b], n, NCCL_UINT32, NCCL_SUM, ctx->comm, ctx->s_side));
+  CU(cudaEventRecord(ctx->ev_red[b], ctx->s_side));
+  const int prev = ctx->red_pending;
+  ctx->red_pending = b;
+  if (prev >= 0) return finalise_snapshot(ctx, thr, prev);
+  return DKB_OK;
+}
+
+int dkb_reduce_flush(dkb_ctx *ctx, const dkb_thresholds *thr) {
+  if (!ctx || !thr) return fail(ctx, DKB_EINVAL, "null argument");
+  if (ctx->red_pending < 0) return DKB_OK;
+  CU(cudaSetDevice(ctx->device));
+  const int b = ctx->red_pending;
+  ctx->red_pending = -1;
+  return finalise_snapshot(ctx, thr, b);
+}
+
+int dkb_reduced_counts_fetch(dkb_ctx *ctx, uint32_t *out) {
+  if (!ctx || !out) return fail(ctx, DKB_EINVAL, "null argument");
+  if (ctx->red_last < 0) return fail(ctx, DKB_ESTATE, "no reduced batch has been finalised yet");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(out, ctx->d_red[ctx->red_last], ctx->n_entries * 3 * 4, cudaMemcpyDeviceToHost,
+                     ctx->s_scan));
+  CU(cudaStreamSynchronize(ctx->s_scan));
   return DKB_OK;
 }
 
@@ -873,6 +1189,48 @@ int dkb_stats_get(dkb_ctx *ctx, dkb_stats *out) {
 int dkb_profile_counters(dkb_ctx *ctx, int enable) {
   if (!ctx) return fail(nullptr, DKB_EINVAL, "ctx is null");
   ctx->prof = enable != 0;
+  return DKB_OK;
+}
+
+int dkb_thread_bind_near_gpu(dkb_ctx *ctx, int *numa_node_out) {
+  if (!ctx) return fail(nullptr, DKB_EINVAL, "ctx is null");
+  const int node = gpu_numa_node(ctx->device);
+  if (numa_node_out) *numa_node_out = node;
+  cpu_set_t set;
+  if (node >= 0 && node_cpus(node, &set)) sched_setaffinity(0, sizeof(set), &set);  // best effort
+  return DKB_OK;
+}
+
+int dkb_host_alloc(dkb_ctx *ctx, size_t bytes, void **out) {
+  if (!ctx || !out) return fail(ctx, DKB_EINVAL, "null argument");
+  *out = nullptr;
+  CU(cudaSetDevice(ctx->device));
+  // allocate (and thereby pin: the pages are populated at once) while this thread runs on,
+  // and prefers memory of, the NUMA node the GPU hangs off; then put the thread back
+  const int node = gpu_numa_node(ctx->device);
+  cpu_set_t old, near;
+  const bool have_old = sched_getaffinity(0, sizeof(old), &old) == 0;
+  const bool moved = node >= 0 && node_cpus(node, &near) && sched_setaffinity(0, sizeof(near), &near) == 0;
+  if (node >= 0) prefer_node(node);
+  void *p = nullptr;
+  const cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (node >= 0) prefer_node(-1);
+  if (moved && have_old) sched_setaffinity(0, sizeof(old), &old);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ctx, DKB_ENOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+  }
+  *out = p;
+  return DKB_OK;
+}
+
+int dkb_host_free(dkb_ctx *ctx, void *p) {
+  if (!p) return DKB_OK;
+  if (ctx) cudaSetDevice(ctx->device);
+  if (cudaFreeHost(p) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ctx, DKB_ECUDA, "cudaFreeHost failed");
+  }
   return DKB_OK;
 }
 

@@ -75,44 +75,43 @@ __global__ void k_apply_dead(const BuildParams B) {
   if (B.dead[i]) B.kt.slots[B.slot_of[i]].z = ENTRY_DEAD;
 }
 
+// Word w of seed-table slot `slot` (8 words per slot; layout in dkb_device.cuh).
+__device__ __forceinline__ uint32_t *slot_word(const SeedTable &T, uint32_t slot, int w) {
+  return reinterpret_cast<uint32_t *>(T.slots) + 8 * (size_t)slot + w;
+}
+
 // Insert a seed into the seed table: the home slot, else the first free slot after it,
 // with the home slot marked ST_MOVED_BIT so that lookups know to walk on.
 __device__ __forceinline__ void seedtab_insert(const SeedTable &T, uint32_t seed) {
-  uint32_t slot = seed_home(seed, T.shift);
+  uint32_t slot = seed_home(seed, T.n_slots);
   bool home = true;
   while (true) {
-    uint32_t old = T.seeds[slot];
+    uint32_t *w0 = slot_word(T, slot, 0);
+    uint32_t old = *reinterpret_cast<volatile uint32_t *>(w0);
     if (old & ST_FREE_BIT) {
-      old = atomicCAS(T.seeds + slot, ST_EMPTY, seed);
+      old = atomicCAS(w0, ST_EMPTY, seed);
       if (old == ST_EMPTY) old = seed;
     }
     if ((old & ST_SEED_BITS) == seed) return;
-    if (home) atomicOr(T.seeds + slot, ST_MOVED_BIT);  // taken by another seed
+    if (home) atomicOr(w0, ST_MOVED_BIT);  // taken by another seed
     home = false;
-    slot = (slot + 1) & T.slot_mask;
+    slot = seed_next(slot, T.n_slots);
   }
 }
 
 // Slot of a seed that is in the table.
 __device__ __forceinline__ uint32_t seedtab_find(const SeedTable &T, uint32_t seed) {
-  uint32_t slot = seed_home(seed, T.shift);
-  while ((T.seeds[slot] & ST_SEED_BITS) != seed) slot = (slot + 1) & T.slot_mask;
+  uint32_t slot = seed_home(seed, T.n_slots);
+  while ((*slot_word(T, slot, 0) & ST_SEED_BITS) != seed) slot = seed_next(slot, T.n_slots);
   return slot;
 }
 
-// Number the occupied slots 0 .. n_seeds - 1 (any order).
-__global__ void k_number_seeds(const SeedTable T, uint32_t n_slots, unsigned int *counter) {
-  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= n_slots) return;
-  if (!(T.seeds[slot] & ST_FREE_BIT)) T.sid[slot] = atomicAdd(counter, 1u);
-}
-
-// Working form of a seed record while the designations are being collected (same 8 words):
-// {info, OR of the windows' bases [3], AND of (bases | not covered) [3], unused}; cov[3] per
-// seed = union of the windows' extents.  k_finish_records turns it into the final form.
+// Working form of a slot's record while the designations are being collected (words 1..7):
+// {info, OR of the windows' bases [3], AND of (bases | not covered) [3]}; cov[3] per slot =
+// union of the windows' extents.  k_finish_records turns it into the final form.
 __device__ __forceinline__ void record_add(uint32_t *rec, uint32_t *cov, int j, uint64_t v, int k,
                                            int E) {
-  atomicOr(rec, 1u << j);
+  atomicOr(rec + 1, 1u << j);
   if (E + k > NB_BASES) return;  // neighbourhood does not fit: records stay all-wild
   const int o = E - j;           // first base of the window inside the neighbourhood
   const unsigned __int128 val = (unsigned __int128)v << (2 * o);
@@ -121,28 +120,50 @@ __device__ __forceinline__ void record_add(uint32_t *rec, uint32_t *cov, int j, 
   for (int i = 0; i < 3; i++) {
     const uint32_t vw = (uint32_t)(val >> (32 * i)), ew = (uint32_t)(ext >> (32 * i));
     if (ew == 0) continue;
-    atomicOr(rec + 1 + i, vw);
-    atomicAnd(rec + 4 + i, vw | ~ew);
+    atomicOr(rec + 2 + i, vw);
+    atomicAnd(rec + 5 + i, vw | ~ew);
     atomicOr(cov + i, ew);
   }
 }
 
-__global__ void k_init_records(uint32_t *rec, uint32_t n_seeds) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_seeds * 8u) return;
-  const uint32_t w = i & 7;
-  rec[i] = w >= 4 && w <= 6 ? 0xFFFFFFFFu : 0u;
+// Every slot free, its record in the (empty) working form.
+__global__ void k_init_slots(const SeedTable T) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per uint4
+  if (i >= 2 * (size_t)T.n_slots) return;
+  T.slots[i] = (i & 1) ? make_uint4(0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu)
+                       : make_uint4(ST_EMPTY, 0u, 0u, 0u);
 }
 
-__global__ void k_finish_records(uint32_t *rec, const uint32_t *cov, uint32_t n_seeds) {
+__global__ void k_finish_records(const SeedTable T, const uint32_t *cov) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_seeds) return;
-  uint32_t *r = rec + (size_t)i * 8;
+  if (i >= T.n_slots) return;
+  uint32_t *r = slot_word(T, i, 0);
+  if (r[0] & ST_FREE_BIT) return;
 #pragma unroll
   for (int w = 0; w < 3; w++) {
-    const uint32_t d = r[1 + w] ^ r[4 + w];               // bases on which the windows disagree
+    const uint32_t d = r[2 + w] ^ r[5 + w];               // bases on which the windows disagree
     const uint32_t t = (d | d >> 1) & 0x55555555u;
-    r[4 + w] = ~cov[(size_t)i * 3 + w] | t | t << 1;      // wild: not covered, or disagreement
+    r[5 + w] = ~cov[(size_t)i * 3 + w] | t | t << 1;      // wild: not covered, or disagreement
+  }
+}
+
+// popcount of n words / number of zero bytes, for the build statistics (out[0], out[1])
+__global__ void k_build_stats(const uint32_t *words, uint32_t n_words, const uint8_t *dead,
+                              uint32_t n_dead, unsigned long long *out) {
+  unsigned long long bits = 0, live = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words;
+       i += (size_t)gridDim.x * blockDim.x)
+    bits += __popc(words[i]);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_dead;
+       i += (size_t)gridDim.x * blockDim.x)
+    live += dead[i] == 0;
+  for (int o = 16; o; o >>= 1) {
+    bits += __shfl_xor_sync(FULL_MASK, bits, o);
+    live += __shfl_xor_sync(FULL_MASK, live, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (bits) atomicAdd(out, bits);
+    if (live) atomicAdd(out + 1, live);
   }
 }
 
@@ -171,7 +192,7 @@ __device__ __forceinline__ void seedset_insert(uint32_t *set, uint32_t mask, uin
 // Three passes (the choice of offsets is the same in each):
 //   ASSIGN_COUNT   add the seeds to `set` (sizing);
 //   ASSIGN_INSERT  record the offsets in the entry's slot, insert the seeds, set their filter bits;
-//   ASSIGN_RECORD  (seeds numbered by k_number_seeds) add offset and window to the seed's record.
+//   ASSIGN_RECORD  add offset and window to the record in the seed's slot.
 enum { ASSIGN_COUNT = 0, ASSIGN_INSERT = 1, ASSIGN_RECORD = 2 };
 __global__ void k_assign_seeds(const BuildParams B, int pass, uint32_t *set, uint32_t set_mask,
                                unsigned int *n_seeds, const SeedTable T, uint32_t *cov,
@@ -233,8 +254,8 @@ __global__ void k_assign_seeds(const BuildParams B, int pass, uint32_t *set, uin
       }
       atomicOr(bloom + bloom_word(h, bloom_words), bloom_bits(seed, h, bloom_words, n_hashes));
     } else {
-      const uint32_t id = T.sid[seedtab_find(T, seed)];
-      record_add(reinterpret_cast<uint32_t *>(T.rec) + (size_t)id * 8, cov + (size_t)id * 3, j, v, k, E);
+      const uint32_t slot = seedtab_find(T, seed);
+      record_add(slot_word(T, slot, 0), cov + (size_t)slot * 3, j, v, k, E);
     }
   }
   if (pass == ASSIGN_INSERT) atomicOr(&B.kt.slots[B.slot_of[i]].w, offs);

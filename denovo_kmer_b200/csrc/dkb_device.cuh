@@ -27,7 +27,7 @@ constexpr size_t SCAN_SMEM_BYTES_GF = SCAN_LISTS_BYTES;
 constexpr int MAX_SEED_LEN = 15;             // 30 bits: leaves SEED_EMPTY outside the seed space
 constexpr uint32_t SEED_MULT = 0x9E3779B1u;  // odd multiplier of the filter hash
 constexpr uint32_t PRE_REHASH = 0x85EBCA6Bu;  // odd: L2-filter hash behind a pre-filter = h * PRE_REHASH
-constexpr uint32_t SEEDTAB_MULT = 0xC2B2AE3Du; // seed bucket = (seed * SEEDTAB_MULT) >> shift
+constexpr uint32_t SEEDTAB_MULT = 0xC2B2AE3Du; // seed slot = mulhi(seed * SEEDTAB_MULT, n_slots)
 constexpr uint32_t SEED_EMPTY = 0xFFFFFFFFu;  // free slot of the sizing set (k_assign_seeds, count_only)
 // Seed-table slot word: bits 0..29 the seed, bit 30 = slot is free, bit 31 = some seed
 // whose home is this slot lives further along (a miss must walk on).  A free slot is the
@@ -49,9 +49,11 @@ __host__ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
   return x;
 }
 
-// home slot of a seed in the exact seed table (multiplicative hash, top bits)
-__host__ __device__ __forceinline__ uint32_t seed_home(uint32_t seed, uint32_t shift) {
-  return (seed * SEEDTAB_MULT) >> shift;
+// home slot of a seed in the exact seed table: multiplicative hash, range-reduced by a
+// multiply-high so that the table need not be a power of two (a table rounded up to one was
+// up to twice the size it had to be, all of it L2 footprint)
+__host__ __device__ __forceinline__ uint32_t seed_home(uint32_t seed, uint32_t n_slots) {
+  return (uint32_t)(((uint64_t)(seed * SEEDTAB_MULT) * n_slots) >> 32);
 }
 
 // Seed filter: a blocked Bloom filter, all bits of a seed inside one 32-bit word.  With
@@ -116,27 +118,29 @@ __device__ __forceinline__ uint64_t ldg_u64_hint(const void *ptr, uint64_t pol) 
 }
 
 // ---- the two lookup structures (both in L2) -----------------------------------
-// Seed table: one uint32 word per slot (see ST_*), open addressing, linear probing, at
-// most 1/8 full.  A lookup is ONE 4-byte load unless the home slot carries ST_MOVED_BIT
-// (about one slot in 100): a seed absent from an unmarked home slot is absent from the table.
-// sid[slot] = dense number of the seed; rec[number] = its 32-byte record (SeedRec).
-struct SeedTable {
-  uint32_t *seeds;
-  uint32_t *sid;
-  uint4 *rec;          // 2 x uint4 per seed
-  uint32_t slot_mask;  // n_slots - 1
-  uint32_t shift;      // 32 - log2(n_slots)
-};
-// Seed record, 8 words: {info, nb[0..2], wild[0..2], 0}.
-//   info  bit j = some key designates this seed at offset j (its window starts j before the seed)
-//   nb    the NEIGHBOURHOOD: the 48 bases from E = k - s before the seed, 2 bits each, stream
-//         order - the union of all windows that designate the seed (needs 2k - s <= 48)
-//   wild  both bits of a base set where the designating keys disagree, or none covers it
+// Seed table: open addressing, linear probing, 32-byte slots = ONE L2 sector that holds the
+// seed AND its record, so a verified seed costs no further dependent load:
+//   word 0   bits 0..29 the seed, bit 30 = slot is free, bit 31 = some seed whose home is
+//            this slot lives further along (a miss must walk on); see ST_*
+//   word 1   info: bit j = some key designates this seed at offset j (its window starts j
+//            bases before the seed)
+//   word 2-4 nb, the NEIGHBOURHOOD: the 48 bases from E = k - s before the seed, 2 bits each,
+//            stream order - the union of all windows that designate the seed (2k - s <= 48)
+//   word 5-7 wild: both bits of a base set where the designating keys disagree, or none covers it
+// A lookup is ONE 4-byte load of word 0 unless the home slot carries ST_MOVED_BIT: a seed
+// absent from an unmarked home slot is absent from the table.
 // A read window can equal a designating key only if the read equals nb on the window's
-// bases outside wild.  Stage C therefore compares the read with nb once (one 32-byte load)
-// and probes the key table only for windows inside the matching run around the seed: an
-// s-mer that equals a seed by chance (1 lookup in 1300 at s = 14 with 200 k seeds) costs a
-// compare instead of ~16 dependent key-table probes that miss L2.
+// bases outside wild.  Stage C therefore compares the read with nb once and probes the key
+// table only for windows inside the matching run around the seed: an s-mer that equals a
+// seed by chance (1 lookup in 1300 at s = 14 with 200 k seeds) costs a compare instead of
+// ~16 dependent key-table probes that miss L2.
+struct SeedTable {
+  uint4 *slots;      // 2 x uint4 per slot
+  uint32_t n_slots;  // any size (not a power of two)
+};
+__host__ __device__ __forceinline__ uint32_t seed_next(uint32_t slot, uint32_t n_slots) {
+  return slot + 1 == n_slots ? 0u : slot + 1;
+}
 constexpr int NB_BASES = 48;
 // Key table: 16-byte slots {key lo, key hi, entry index, packed designated
 // offsets}, buckets of 2 slots = one 32-byte L2 sector (two LDG.128), a
@@ -165,10 +169,20 @@ __host__ __device__ __forceinline__ uint32_t slot_offset(uint32_t packed, int or
 }
 
 // ---- parameters of one scan launch -------------------------------------------
-struct ScanParams {
+// A launch scans up to MAX_SEGMENTS packed streams (e.g. the three samples of a trio) one
+// after the other in one grid: work units are numbered across the segments.
+constexpr int MAX_SEGMENTS = 4;
+struct ScanSegment {
   const uint32_t *bases;  // 2-bit stream, 16 positions per word
   const uint32_t *mask;   // 1-bit validity stream, 32 positions per word
+  uint32_t *counts;       // the sample's [n_entries] counters
   uint32_t n_pos, n_bwords, n_mwords, n_tiles;
+  uint32_t unit_begin;    // first work unit (tile, or macro tile) of this segment
+  uint32_t unit_end;      // first work unit AFTER this segment
+};
+struct ScanParams {
+  ScanSegment seg[MAX_SEGMENTS];
+  int n_seg;
   const uint32_t *bloom;  // seed filter: BLOOM_WORDS words copied into shared memory per CTA,
                           // or (large candidate sets) bloom_words words probed in L2
   uint32_t bloom_words;
@@ -183,7 +197,6 @@ struct ScanParams {
   uint32_t four;       // = 4, opaque to the compiler: keeps the filter address on the FMA pipe
   uint32_t pw[32];     // pw[n] = 2^n, opaque too: multiplies by these stay on the FMA pipe
   uint32_t filter_words;  // = BLOOM_WORDS (shared-memory mode), as a run-time operand of the wide multiply
-  uint32_t *counts;    // this sample's [n_entries] counters
   int k, s;
   unsigned long long *prof;  // 4 counters or nullptr
 };

@@ -19,8 +19,7 @@
 
 #ifndef DKB_X
 // Timing experiments only, wrong counts (scripts/ab_build.sh; DESIGN.md §4 "where the time goes"):
-// 1 rounds without their load, 2 no rounds, 3-5 round loads confined to 4 B / 16 KB / 1 MB,
-// 6 no stage C.
+// 1 rounds without their load, 2 no rounds, 6 no stage C.
 #define DKB_X 0
 #endif
 
@@ -36,6 +35,8 @@ struct ScanWarp {
   static constexpr int SUB = MACRO ? 32 / LPT : 1;   // sub-tiles per macro tile
   static constexpr bool LOCAL = D == 2 || D == 4;    // lane-local hit verification
   const ScanParams &P;
+  int cur = 0;  // segment (packed stream) the warp is working on; its fields are read from
+                // the parameter block where needed rather than held in registers
   const uint32_t *filt;
   uint16_t *hl;  // filter-hit ids of the current tile: lane << 6 | lookup index
   uint64_t *cq;  // ring of verified seeds: seed-table slot << 32 | position
@@ -53,10 +54,10 @@ struct ScanWarp {
       : P(p), filt(f), hl(h), cq(c), lane(l), lt_mask((1u << l) - 1), zero(p.four >> 3) {}
 
   __device__ __forceinline__ uint32_t ld_bases(uint32_t wi) const {
-    return wi < P.n_bwords ? __ldg(P.bases + wi) : 0u;
+    return wi < P.seg[cur].n_bwords ? __ldg(P.seg[cur].bases + wi) : 0u;
   }
   __device__ __forceinline__ uint32_t ld_mask(uint32_t wi) const {
-    return wi < P.n_mwords ? __ldg(P.mask + wi) : 0u;
+    return wi < P.seg[cur].n_mwords ? __ldg(P.seg[cur].mask + wi) : 0u;
   }
 
   // ---- stage C: the candidate windows of up to n verified seeds --------------------
@@ -71,16 +72,17 @@ struct ScanWarp {
     const uint64_t key = fwd <= rc ? fwd : rc;
     const int ori = fwd <= rc ? 0 : 1;
     uint32_t bk = key_bucket(key, P.kt.bucket_mask);
+    uint32_t *const counts = P.seg[cur].counts;
     while (true) {
       const uint4 *bp = P.kt.slots + bk * KBUCKET;
       const uint4 s0 = ldg_v4_hint(bp, keep), s1 = ldg_v4_hint(bp + 1, keep);
       const uint64_t k0 = slot_key(s0), k1 = slot_key(s1);
       if (k0 == key && s0.z != ENTRY_DEAD && slot_offset(s0.w, ori, j % D, D) == (uint32_t)j) {
-        atomicAdd(P.counts + s0.z, 1u);
+        atomicAdd(counts + s0.z, 1u);
         if (PROF) n_hit++;
       }
       if (k1 == key && s1.z != ENTRY_DEAD && slot_offset(s1.w, ori, j % D, D) == (uint32_t)j) {
-        atomicAdd(P.counts + s1.z, 1u);
+        atomicAdd(counts + s1.z, 1u);
         if (PROF) n_hit++;
       }
       if (k0 == KEY_EMPTY || k1 == KEY_EMPTY) break;  // bucket not full: nothing spilled
@@ -102,32 +104,36 @@ struct ScanWarp {
     const int k = P.k, s = P.s, E = k - s;
     const uint64_t km = kmer_mask(k);
     uint32_t info = 0, p = 0, rn0 = 0, rn1 = 0, rn2 = 0;
+    const uint32_t n_pos = P.seg[cur].n_pos;
     if ((uint32_t)lane < n) {
       const uint64_t e = cq[(ch + lane) & (CQ_CAP - 1)];
       p = (uint32_t)e;
       const uint32_t start = p > (uint32_t)E ? p - (uint32_t)E : 0u;
       const uint32_t bw0 = start >> 4, mw0 = start >> 5;
-      const uint32_t id = ldg_u32_hint(P.st.sid + (uint32_t)(e >> 32), keep);
+      // the seed's slot = its record: the sector stage B already touched
+      const uint4 *rp = P.st.slots + 2 * (size_t)(uint32_t)(e >> 32);
+      const uint4 r0 = ldg_v4_hint(rp, keep), r1 = ldg_v4_hint(rp + 1, keep);
+      const uint32_t nb0 = r0.z, nb1 = r0.w, nb2 = r1.x, wd0 = r1.y, wd1 = r1.z, wd2 = r1.w;
       uint32_t b[5], m[3];
 #pragma unroll
       for (int i = 0; i < 5; i++) b[i] = ld_bases(bw0 + i);
 #pragma unroll
       for (int i = 0; i < 3; i++) m[i] = ld_mask(mw0 + i);
-      const uint4 r0 = ldg_v4_hint(P.st.rec + 2 * (size_t)id, keep);
-      const uint4 r1 = ldg_v4_hint(P.st.rec + 2 * (size_t)id + 1, keep);
-      info = r0.x;
+      info = r0.y;
       if (p >= (uint32_t)E && E + k <= NB_BASES) {
         // the read's neighbourhood (base 0 = p - E) and its mismatches, 2 bits per base
         const uint32_t sh = 2 * (start & 15);
         rn0 = __funnelshift_r(b[0], b[1], sh);
         rn1 = __funnelshift_r(b[1], b[2], sh);
         rn2 = __funnelshift_r(b[2], b[3], sh);
-        const uint32_t mm0 = (rn0 ^ r0.y) & ~r1.x, mm1 = (rn1 ^ r0.z) & ~r1.y, mm2 = (rn2 ^ r0.w) & ~r1.z;
+        const uint32_t mm0 = (rn0 ^ nb0) & ~wd0, mm1 = (rn1 ^ nb1) & ~wd1, mm2 = (rn2 ^ nb2) & ~wd2;
         const unsigned __int128 mm = (unsigned __int128)mm2 << 64 | (unsigned __int128)mm1 << 32 | mm0;
         // invalid positions (N, low quality, read separators, end of stream), 1 bit per base
         const uint32_t mo = start & 31;
         uint64_t inv = ~((uint64_t)__funnelshift_r(m[1], m[2], mo) << 32 | __funnelshift_r(m[0], m[1], mo));
-        if (P.n_pos - start < (uint32_t)NB_BASES) inv |= ~0ull << (P.n_pos - start);  // end of stream
+        // end of stream: nothing at or beyond n_pos is a base, whatever the padding bits say
+        if (start >= n_pos) inv = ~0ull;
+        else if (n_pos - start < (uint32_t)NB_BASES) inv |= ~0ull << (n_pos - start);
         inv &= (1ull << NB_BASES) - 1;
         // R = first bad base at or after the seed's end, Lm = last one before its start; nothing
         // beyond base E + k is covered by a window, so both searches fit 64 bits
@@ -151,7 +157,7 @@ struct ScanWarp {
           info &= info - 1;
           if (p < (uint32_t)j) continue;
           const uint32_t w = p - (uint32_t)j;
-          if (w + (uint32_t)k > P.n_pos) continue;
+          if (w + (uint32_t)k > n_pos) continue;
           const uint32_t wo = w - (mw0 << 5);  // < 64
           const uint32_t mbits = wo < 32 ? __funnelshift_r(m[0], m[1], wo)
                                          : __funnelshift_r(m[1], m[2], wo - 32);
@@ -215,13 +221,18 @@ struct ScanWarp {
     asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]));
   }
 
+  // word 0 of a seed-table slot (the seed and its flags)
+  __device__ __forceinline__ uint32_t ld_slot_word(uint32_t slot) const {
+    return ldg_u32_hint(reinterpret_cast<const uint32_t *>(P.st.slots) + 8 * (size_t)slot, keep);
+  }
+
   // Slow half of a seed-table lookup: the home slot holds another seed and carries
   // ST_MOVED_BIT, so the seed may sit further along (linear probing, ends at a free slot).
   __device__ __forceinline__ bool walk(uint32_t x, uint32_t &slot) const {
     uint32_t b = slot;
     while (true) {
-      b = (b + 1) & P.st.slot_mask;
-      const uint32_t v = ldg_u32_hint(P.st.seeds + b, keep);
+      b = seed_next(b, P.st.n_slots);
+      const uint32_t v = ld_slot_word(b);
       if ((v & ST_SEED_BITS) == x) {
         slot = b;
         return true;
@@ -293,7 +304,7 @@ struct ScanWarp {
       const uint32_t i = 31u - ((lidx >> (8 * r)) & 31u);
       bool found = has && ((v ^ x) & ST_SEED_BITS) == 0;
       const bool moved = has && !found;  // flagged without a match: ST_MOVED_BIT
-      uint32_t slot = seed_home(x, P.st.shift);
+      uint32_t slot = seed_home(x, P.st.n_slots);
       if (__any_sync(FULL_MASK, moved)) {
         if (moved) found = walk(x, slot);
         __syncwarp();
@@ -321,14 +332,8 @@ struct ScanWarp {
         a &= ~(1u << (b & 31));
         const uint32_t x = cut_seed(w, b);
         lx[r] = x;
-#if DKB_X == 3
-        if (has) lv[r] = ldg_u32_hint(P.st.seeds + (seed_home(x, P.st.shift) & 0), keep);
-#elif DKB_X == 4
-        if (has) lv[r] = ldg_u32_hint(P.st.seeds + (seed_home(x, P.st.shift) & 4095), keep);
-#elif DKB_X == 5
-        if (has) lv[r] = ldg_u32_hint(P.st.seeds + (seed_home(x, P.st.shift) & 0x3FFFF), keep);
-#elif DKB_X != 1
-        if (has) lv[r] = ldg_u32_hint(P.st.seeds + seed_home(x, P.st.shift), keep);
+#if DKB_X != 1
+        if (has) lv[r] = ld_slot_word(seed_home(x, P.st.n_slots));
 #endif
         lidx |= (b & 31) << (8 * r);
       }
@@ -376,8 +381,8 @@ struct ScanWarp {
       pend_p = tile_base + (idx / LPT) * WTILE + src * CHUNK + (idx % LPT) * D;
       const uint32_t wi = pend_p >> 4;
       pend_x = __funnelshift_r(ld_bases(wi), ld_bases(wi + 1), 2 * (pend_p & 15)) & P.seed_mask;
-      pend_b = seed_home(pend_x, P.st.shift);
-      if (act) pend_v = ldg_u32_hint(P.st.seeds + pend_b, keep);
+      pend_b = seed_home(pend_x, P.st.n_slots);
+      if (act) pend_v = ld_slot_word(pend_b);
       pend_n = n;
       return;
     }
@@ -392,8 +397,8 @@ struct ScanWarp {
     if (c == 3) { lo = v[3]; hi = v[4]; }
     pend_x = __funnelshift_r(lo, hi, 2 * (q & 15)) & P.seed_mask;
     pend_p = tile_base + src * CHUNK + q;
-    pend_b = seed_home(pend_x, P.st.shift);
-    if (act) pend_v = ldg_u32_hint(P.st.seeds + pend_b, keep);
+    pend_b = seed_home(pend_x, P.st.n_slots);
+    if (act) pend_v = ld_slot_word(pend_b);
     pend_n = n;
   }
 
@@ -591,29 +596,60 @@ struct ScanWarp {
   }
 };
 
+// ---- stream loads -------------------------------------------------------------------
+// DKB_STREAM_LD selects how the macro path (strides 8, 16) reads the stream: 0 = plain
+// read-only loads at normal L2 priority (filter hits re-read their bases from L2 soon after),
+// 1 = evict-first (the stream is read once and must not push the filter and tables out of L2).
+#ifndef DKB_STREAM_LD
+#define DKB_STREAM_LD 1
+#endif
+__device__ __forceinline__ uint4 ld_stream_v4(const uint32_t *p) {
+#if DKB_STREAM_LD == 1
+  return __ldcs(reinterpret_cast<const uint4 *>(p));
+#else
+  return __ldg(reinterpret_cast<const uint4 *>(p));
+#endif
+}
+
 // tile -> registers.  Streaming (evict-first) loads: the stream is read once
 // and must not push the seed / key tables out of L2.
-__device__ __forceinline__ void load_tile(const ScanParams &P, uint32_t tile, int lane,
+__device__ __forceinline__ void load_tile(const ScanSegment &S, uint32_t tile, int lane,
                                           uint32_t (&w)[5]) {
   const uint32_t wi = tile * WTILE_WORDS + lane * 4;
-  if (wi + 4 <= P.n_bwords) {
-    const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(P.bases + wi));
+  if (wi + 4 <= S.n_bwords) {
+    const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(S.bases + wi));
     w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
   } else {
 #pragma unroll
-    for (int i = 0; i < 4; i++) w[i] = wi + i < P.n_bwords ? P.bases[wi + i] : 0u;
+    for (int i = 0; i < 4; i++) w[i] = wi + i < S.n_bwords ? S.bases[wi + i] : 0u;
   }
   // w[4] of lane 31 = first word of the next warp tile; the other lanes get
   // theirs from lane + 1 in halo_finish(), AFTER the loads have landed, so the
   // prefetch of the next tile never stalls on a shuffle.
   w[4] = 0;
-  if (lane == 31) w[4] = wi + 4 < P.n_bwords ? __ldg(P.bases + wi + 4) : 0u;
+  if (lane == 31) w[4] = wi + 4 < S.n_bwords ? __ldg(S.bases + wi + 4) : 0u;
 }
 
 __device__ __forceinline__ void halo_finish(int lane, uint32_t (&w)[5]) {
   const uint32_t up = __shfl_down_sync(FULL_MASK, w[0], 1);
   if (lane != 31) w[4] = up;
 }
+
+// Work units (tiles, or macro tiles at strides 8 / 16) are numbered across the launch's
+// segments; a warp takes units g, g + n_warps, ...  seg = the segment unit belongs to
+// (n_seg once the units are used up).
+struct UnitCursor {
+  uint32_t unit;
+  int seg;
+  __device__ __forceinline__ void settle_seg(const ScanParams &P) {
+    while (seg < P.n_seg && unit >= P.seg[seg].unit_end) seg++;
+  }
+  __device__ __forceinline__ bool live(const ScanParams &P) const { return seg < P.n_seg; }
+  // index of the unit inside its segment
+  __device__ __forceinline__ uint32_t local(const ScanParams &P) const {
+    return unit - P.seg[seg].unit_begin;
+  }
+};
 
 template <int D, int NH, bool GF, bool PROF>
 __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
@@ -633,6 +669,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
   ScanWarp<D, NH, GF, PROF> W(P, filt, hl_all + warp * HL_CAP, cq_all + warp * CQ_CAP, lane);
 
   const uint32_t n_warps = gridDim.x * SCAN_WARPS;
+  UnitCursor c{warp * gridDim.x + blockIdx.x, 0};  // consecutive units on different SMs
+  c.settle_seg(P);
+  W.cur = c.live(P) ? c.seg : 0;
   if constexpr (ScanWarp<D, NH, GF, PROF>::MACRO) {
     // Strides 8 / 16: a macro tile = SUB sub-tiles of 2048 positions (32 lookups per lane),
     // read in groups of GS sub-tiles (GS LDG.128 per lane in flight, 1-2 KB per warp), with
@@ -640,43 +679,40 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
     constexpr int SUB = ScanWarp<D, NH, GF, PROF>::SUB, LPT = ScanWarp<D, NH, GF, PROF>::LPT;
     constexpr int GS = 2, GPM = SUB / GS;  // sub-tiles per group, groups per macro tile
     constexpr bool HALO = D < 16;          // at stride 16 every seed lies inside one word
-    const uint32_t n_macro = (P.n_tiles + SUB - 1) / SUB;
-    auto load_group = [&](uint32_t t0, uint4 (&v)[GS], uint32_t &edge) {
+    auto load_group = [&](const ScanSegment &S, uint32_t t0, uint4 (&v)[GS], uint32_t &edge) {
       const uint32_t wb = t0 * WTILE_WORDS + lane * 4;
-      if ((t0 + GS) * WTILE_WORDS + 4 <= P.n_bwords) {
+      if ((t0 + GS) * WTILE_WORDS + 4 <= S.n_bwords) {
 #pragma unroll
-        for (int j = 0; j < GS; j++)  // normal L2 priority: filter hits re-read these sectors soon
-          v[j] = __ldg(reinterpret_cast<const uint4 *>(P.bases + wb + j * WTILE_WORDS));
+        for (int j = 0; j < GS; j++) v[j] = ld_stream_v4(S.bases + wb + j * WTILE_WORDS);
         edge = 0;
-        if (HALO && lane == 31) edge = __ldg(P.bases + (t0 + GS) * WTILE_WORDS);
+        if (HALO && lane == 31) edge = __ldg(S.bases + (t0 + GS) * WTILE_WORDS);
       } else {  // the stream ends inside this group
 #pragma unroll
         for (int j = 0; j < GS; j++) {
           const uint32_t q = wb + j * WTILE_WORDS;
-          v[j].x = q < P.n_bwords ? P.bases[q] : 0u;
-          v[j].y = q + 1 < P.n_bwords ? P.bases[q + 1] : 0u;
-          v[j].z = q + 2 < P.n_bwords ? P.bases[q + 2] : 0u;
-          v[j].w = q + 3 < P.n_bwords ? P.bases[q + 3] : 0u;
+          v[j].x = q < S.n_bwords ? S.bases[q] : 0u;
+          v[j].y = q + 1 < S.n_bwords ? S.bases[q + 1] : 0u;
+          v[j].z = q + 2 < S.n_bwords ? S.bases[q + 2] : 0u;
+          v[j].w = q + 3 < S.n_bwords ? S.bases[q + 3] : 0u;
         }
         const uint32_t e = (t0 + GS) * WTILE_WORDS;
-        edge = HALO && e < P.n_bwords ? P.bases[e] : 0u;
+        edge = HALO && e < S.n_bwords ? S.bases[e] : 0u;
       }
     };
-    uint32_t macro = warp * gridDim.x + blockIdx.x;  // consecutive units on different SMs
     int g = 0;
     uint4 nxt[GS];
     uint32_t nxt_edge = 0;
-    if (macro < n_macro) load_group(macro * SUB, nxt, nxt_edge);
+    if (c.live(P)) load_group(P.seg[c.seg], c.local(P) * SUB, nxt, nxt_edge);
     uint32_t acc = 0;
-    while (macro < n_macro) {
+    while (c.live(P)) {
       uint4 v[GS];
 #pragma unroll
       for (int j = 0; j < GS; j++) v[j] = nxt[j];
       const uint32_t edge = nxt_edge;
-      const uint32_t cur_macro = macro;
+      const uint32_t cur_macro = c.local(P);
       const bool last_group = g == GPM - 1;
-      if (last_group) { macro += n_warps; g = 0; } else { g++; }
-      if (macro < n_macro) load_group(macro * SUB + g * GS, nxt, nxt_edge);
+      if (last_group) { c.unit += n_warps; c.settle_seg(P); g = 0; } else { g++; }
+      if (c.live(P)) load_group(P.seg[c.seg], c.local(P) * SUB + g * GS, nxt, nxt_edge);
 #pragma unroll
       for (int j = 0; j < GS; j++) {
         uint32_t w[5] = {v[j].x, v[j].y, v[j].z, v[j].w, 0};
@@ -700,12 +736,15 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
         const uint32_t w0[5] = {0, 0, 0, 0, 0};
         W.handle_hits(acc, 0, w0, cur_macro * SUB * WTILE);
         acc = 0;
+        if (c.live(P) && c.seg != W.cur) {  // the warp's next unit lies in another stream
+          W.drain();
+          W.cur = c.seg;
+        }
       }
     }
   } else {
-  uint32_t tile = warp * gridDim.x + blockIdx.x;  // consecutive tiles on different SMs
   uint32_t nxt[5];
-  if (tile < P.n_tiles) load_tile(P, tile, lane, nxt);
+  if (c.live(P)) load_tile(P.seg[c.seg], c.local(P), lane, nxt);
   if constexpr (ScanWarp<D, NH, GF, PROF>::LOCAL) {
     // Rotated loop: the table loads of tile t (its rounds) are issued at the top of
     // iteration t + 1, right after the prefetched words of tile t + 1 have been settled and
@@ -714,33 +753,48 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
     // scoreboard there).
     uint32_t w[5] = {0, 0, 0, 0, 0};
     uint32_t acc_prev = 0, base_prev = 0;
-    for (; tile < P.n_tiles; tile += n_warps) {
+    while (c.live(P)) {
       W.settle(nxt);
+      if (c.seg != W.cur) {  // first tile of another stream: finish the previous one's hits
+        W.start_local(acc_prev, w, base_prev);
+        W.drain();
+        acc_prev = 0;
+        W.cur = c.seg;
+      }
 #if DKB_X != 2
       W.start_local(acc_prev, w, base_prev);
 #endif
 #pragma unroll
       for (int i = 0; i < 5; i++) w[i] = nxt[i];
-      if (tile + n_warps < P.n_tiles) load_tile(P, tile + n_warps, lane, nxt);
+      base_prev = c.local(P) * WTILE;
+      c.unit += n_warps;
+      c.settle_seg(P);
+      if (c.live(P)) load_tile(P.seg[c.seg], c.local(P), lane, nxt);
       halo_finish(lane, w);
       uint32_t acc1;
       W.stage_a(w, acc_prev, acc1);
       W.resolve_local(acc_prev);
-      base_prev = tile * WTILE;
     }
     W.start_local(acc_prev, w, base_prev);  // the last tile's hits; drain() resolves them
   } else {
-  for (; tile < P.n_tiles; tile += n_warps) {
+  while (c.live(P)) {
     uint32_t w[5];
 #pragma unroll
     for (int i = 0; i < 5; i++) w[i] = nxt[i];
-    if (tile + n_warps < P.n_tiles) load_tile(P, tile + n_warps, lane, nxt);
+    const uint32_t tile_base = c.local(P) * WTILE;
+    c.unit += n_warps;
+    c.settle_seg(P);
+    if (c.live(P)) load_tile(P.seg[c.seg], c.local(P), lane, nxt);
     halo_finish(lane, w);
     uint32_t acc0, acc1;
     W.stage_a(w, acc0, acc1);
     W.consume_pending(acc0 | acc1);
     W.settle(nxt);
-    W.handle_hits(acc0, acc1, w, tile * WTILE);
+    W.handle_hits(acc0, acc1, w, tile_base);
+    if (c.live(P) && c.seg != W.cur) {  // the warp's next tile lies in another stream
+      W.drain();
+      W.cur = c.seg;
+    }
   }
   }
   }

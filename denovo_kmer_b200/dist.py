@@ -1,10 +1,8 @@
 """Multi-GPU plumbing: one process per GPU, read batches sharded across ranks, the
 spanning-k-mer table replicated, and ONE sum-allreduce of the per-entry count vector
-(north_star).  No other collective exists on the path.  CountPipeline overlaps
-that allreduce with the next batch's scan.
-
-The same functions run on `gloo` with CPU tensors (tests, world_size 2) and on `nccl`
-with a tensor view of the library's device counters.
+(north_star).  No other collective exists on the path, and it is made by
+libdkb.so itself (dkb_comm_init / dkb_counts_allreduce / dkb_reduce_push: ncclAllReduce on
+the library's streams).  This module only shards the work and hands the NCCL id round.
 """
 import os
 
@@ -32,8 +30,8 @@ class _DevArray:
 
 
 def counts_tensor(kc):
-    """torch int32 view (no copy) of the context's [3][n_entries] device counters.
-    Sums wrap mod 2^32 exactly like the uint32 counters do."""
+    """torch int32 view (no copy) of the context's [3][n_entries] device counters (tests and
+    checks; the product's own sum over ranks never leaves the library)."""
     import torch
     ptr, n = kc.entry_counts_device()
     if n == 0:
@@ -41,66 +39,45 @@ def counts_tensor(kc):
     return torch.as_tensor(_DevArray(ptr, n), device=f"cuda:{kc.device}")
 
 
-def allreduce_counts(t, group=None):
-    """In-place sum over ranks of a count tensor (device int32 view, or CPU int64/int32)."""
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-    return t
+def bootstrap_comm(kc, rank: int, world: int, group=None):
+    """Give the context its NCCL communicator (inside libdkb.so).  The 128-byte id is made by
+    rank 0 and handed round with one torch.distributed broadcast on whatever process group
+    the launcher set up (gloo or nccl) - bootstrap only; the counters never go through torch."""
+    if world == 1:
+        return
+    import torch.distributed as tdist
+    from . import api
+    box = [api.comm_unique_id() if rank == 0 else None]
+    tdist.broadcast_object_list(box, src=0, group=group)
+    kc.comm_init(box[0], rank, world)
 
 
 def allreduce_counts_numpy(counts: np.ndarray, group=None) -> np.ndarray:
-    """Host variant used by the gloo tests: uint32/uint64 array -> summed copy."""
+    """Host-side sum over ranks (gloo tests of the sharding logic): uint32/uint64 array ->
+    summed copy.  The GPU path does not use this: its sum is ncclAllReduce inside the library."""
     import torch
+    import torch.distributed as tdist
     t = torch.from_numpy(counts.astype(np.int64))
-    allreduce_counts(t, group)
+    if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size(group) > 1:
+        tdist.all_reduce(t, op=tdist.ReduceOp.SUM, group=group)
     return t.numpy().astype(counts.dtype)
 
 
 class CountPipeline:
-    """Overlap the allreduce of one batch's counters with the scan of the next batch.
+    """Overlap the sum over ranks of one batch's counters with the scan of the next batch -
+    a thin caller of dkb_reduce_push / dkb_reduce_flush (the double-buffered snapshot, the
+    side stream and the ncclAllReduce all live in libdkb.so).
 
-    push() - call it when a batch's scans have been submitted - copies the context's counters
-    into one of two buffers on the scan stream and starts the sum over ranks on a side
-    stream; the PREVIOUS batch's reduced buffer is then finalised (kernel 3) on the scan
-    stream, behind this batch's scans, by which time its allreduce has long finished.
-    flush() finalises the last batch.  With world size 1 the allreduce is a no-op and the
-    results equal plain finalise().
-    """
+    push() - call it when a batch's scans have been submitted - snapshots the counters and
+    starts their sum; the PREVIOUS batch is finalised (kernel 3) behind this batch's scans.
+    flush() finalises the last batch.  Without a communicator (one GPU) the results equal
+    plain finalise()."""
 
-    def __init__(self, kc, thresholds, group=None):
-        import torch
-        self.kc, self.thr, self.group = kc, thresholds, group
-        self.dev = torch.device(f"cuda:{kc.device}")
-        self.counts = counts_tensor(kc)
-        self.bufs = [torch.empty_like(self.counts) for _ in range(2)]
-        self.scan = torch.cuda.ExternalStream(kc.scan_stream(), device=self.dev)
-        self.side = torch.cuda.Stream(device=self.dev)
-        self.copied = [torch.cuda.Event() for _ in range(2)]
-        self.reduced = [torch.cuda.Event() for _ in range(2)]
-        self.i = 0
-        self.pending = None  # buffer index whose finalise is still due
+    def __init__(self, kc, thresholds):
+        self.kc, self.thr = kc, thresholds
 
     def push(self):
-        import torch
-        b = self.i & 1
-        self.i += 1
-        with torch.cuda.stream(self.scan):
-            self.bufs[b].copy_(self.counts, non_blocking=True)
-            self.copied[b].record(self.scan)
-        with torch.cuda.stream(self.side):
-            self.side.wait_event(self.copied[b])
-            allreduce_counts(self.bufs[b], self.group)
-            self.reduced[b].record(self.side)
-        prev, self.pending = self.pending, b
-        return prev
-
-    def finalise(self, b):
-        if b is None:
-            return
-        self.scan.wait_event(self.reduced[b])
-        self.kc.finalise_launch(self.thr, counts_ptr=self.bufs[b].data_ptr())
+        self.kc.reduce_push(self.thr)
 
     def flush(self):
-        b, self.pending = self.pending, None
-        self.finalise(b)
+        self.kc.reduce_flush(self.thr)

@@ -53,7 +53,8 @@ enum {
   DKB_ECUDA = 2,  /* CUDA runtime error (see dkb_last_error) */
   DKB_ENOMEM = 3, /* host or device allocation failed */
   DKB_ESTATE = 4, /* call out of order (e.g. submit before table_build) */
-  DKB_ENODEV = 5  /* no usable sm_100 device; there is no CPU fallback */
+  DKB_ENODEV = 5, /* no usable sm_100 device; there is no CPU fallback */
+  DKB_ENCCL = 6   /* NCCL error, or libnccl.so.2 cannot be loaded (multi-GPU calls only) */
 };
 
 typedef struct dkb_ctx dkb_ctx;
@@ -86,9 +87,9 @@ typedef struct dkb_tuning {
   int stride;       /* D: probe every D-th stream position (1, 2, 4, 8 or 16); 0 = auto */
   int bloom_hashes; /* 1..4 bits per seed in the seed filter; 0 = auto */
   int filter_mode;  /* 1 = filter in shared memory (small candidate sets), 2 = filter in L2
-                       (strides 2..16, 1..2 hashes; the library decides whether a 128 KB
-                       shared-memory pre-filter goes in front of it, env DKB_PREFILTER_WORDS
-                       overrides); 0 = auto */
+                       (strides 2..16, 1..2 hashes; the library decides whether a 139 KB
+                       (35 584-word) shared-memory pre-filter goes in front of it, env
+                       DKB_PREFILTER_WORDS overrides); 0 = auto */
 } dkb_tuning;
 
 /* ---- library ---------------------------------------------------------- */
@@ -159,9 +160,17 @@ int dkb_batch_submit(dkb_ctx *ctx, const uint32_t *bases2, const uint32_t *mask1
  * one byte per base at qual[offsets[r]..].  Same stream, bit for bit, as dkb_pack_reads. */
 int dkb_batch_submit_reads(dkb_ctx *ctx, const uint8_t *seq, int seq_format, const uint8_t *qual,
                            const uint64_t *offsets, size_t n_reads, int min_baseq, int sample);
-/* Device-resident buffers (16-byte aligned, dkb_stream_*_words long). */
+/* Device-resident buffers: d_bases2 16-byte aligned, d_mask1 4-byte aligned, each
+ * dkb_stream_*_words long.  Flags at positions >= n_positions are ignored. */
 int dkb_batch_submit_device(dkb_ctx *ctx, const uint32_t *d_bases2, const uint32_t *d_mask1,
                             uint64_t n_positions, int sample);
+/* Up to DKB_MAX_MULTI device-resident streams (e.g. the three samples of a trio) in ONE kernel
+ * launch; batch i goes into the counters of samples[i].  Same alignment rules; a batch of 0
+ * positions is skipped.  Worth it for short batches, where a launch costs as much as the scan. */
+#define DKB_MAX_MULTI 4
+int dkb_batch_submit_device_multi(dkb_ctx *ctx, int n_batches, const uint32_t *const *d_bases2,
+                                  const uint32_t *const *d_mask1, const uint64_t *n_positions,
+                                  const int *samples);
 int dkb_sync(dkb_ctx *ctx);
 int dkb_counts_reset(dkb_ctx *ctx);
 
@@ -181,6 +190,42 @@ int dkb_finalise_from(dkb_ctx *ctx, const dkb_thresholds *thr, const uint32_t *d
  * [n_variants][DKB_N_ALLELES]; calls: [n_variants].  Any pointer may be NULL. */
 int dkb_results_fetch(dkb_ctx *ctx, uint32_t *hits, uint32_t *distinct, uint32_t *n_kmers,
                       uint8_t *calls);
+
+/* ---- pinned staging next to the GPU ------------------------------------------ */
+/* Page-locked host memory for the packed batches, allocated on the NUMA node the GPU's PCIe
+ * slot belongs to (the calling thread is moved there for the allocation and moved back).  With
+ * eight ranks pushing batches at once, buffers on the wrong socket halve the H2D rate.
+ * dkb_thread_bind_near_gpu pins the CALLING thread (the one that packs and submits) to that
+ * node's CPUs for good; *numa_node_out (may be NULL) gets the node, -1 if unknown. */
+int dkb_host_alloc(dkb_ctx *ctx, size_t bytes, void **out);
+int dkb_host_free(dkb_ctx *ctx, void *p);
+int dkb_thread_bind_near_gpu(dkb_ctx *ctx, int *numa_node_out);
+
+/* ---- multi-GPU: read batches sharded over ranks, ONE sum of the counters ------ */
+/* One process (or thread) per GPU, each with its own context and its own slice of the read
+ * batches; the table is built identically on every rank.  The per-entry counters are summed
+ * over ranks with a single NCCL allreduce (libnccl.so.2 is loaded on first use; without it
+ * these calls return DKB_ENCCL and everything else works).
+ *   rank 0: dkb_comm_unique_id(id)  -> send the DKB_COMM_ID_BYTES to every rank (MPI, TCP, a file ...)
+ *   all   : dkb_comm_init(ctx, id, rank, world)
+ * Simple form: scan, then dkb_counts_allreduce (in place, on the scan stream), dkb_finalise.
+ * Overlapped form, for a sequence of independent batches (trios, regions): after a batch's
+ * scans dkb_reduce_push snapshots the counters and starts the sum on a side stream; the
+ * caller resets the counters and submits the next batch at once; the push of batch i also
+ * queues kernel 3 for batch i-1 behind the scans just submitted, by which time that sum has
+ * long finished.  dkb_reduce_flush finalises the last batch; dkb_results_fetch then returns
+ * its results and dkb_reduced_counts_fetch its summed counters.  With no communicator (one
+ * GPU) both forms run without NCCL and equal plain dkb_finalise. */
+#define DKB_COMM_ID_BYTES 128
+int dkb_comm_unique_id(void *id_out);
+int dkb_comm_init(dkb_ctx *ctx, const void *id, int rank, int world);
+int dkb_comm_destroy(dkb_ctx *ctx);
+/* rank, communicator size as NCCL reports it, NCCL version (0 without a communicator) */
+int dkb_comm_info(const dkb_ctx *ctx, int *rank, int *world, int *nccl_version);
+int dkb_counts_allreduce(dkb_ctx *ctx);
+int dkb_reduce_push(dkb_ctx *ctx, const dkb_thresholds *thr);
+int dkb_reduce_flush(dkb_ctx *ctx, const dkb_thresholds *thr);
+int dkb_reduced_counts_fetch(dkb_ctx *ctx, uint32_t *out);
 
 /* ---- introspection (bench / tests) --------------------------------------- */
 typedef struct dkb_stats {

@@ -146,7 +146,9 @@ void orc_set_free(orc_set *s) {
 void orc_set_live(const orc_set *s, uint8_t *live_out) { memcpy(live_out, s->live, s->n_entries); }
 
 /* counter.rs: count, for every entry, how many read k-mers equal its key.
- * counts[n_entries] is ADDED to.  Reads are split over n_threads threads. */
+ * counts[n_entries] is ADDED to.  Reads are split over n_threads threads; matches are a
+ * fraction of a percent of the k-mers, so the threads add into the one shared array with
+ * atomic increments (no per-thread copy of the counters to allocate and merge per call). */
 void orc_count_reads(const orc_set *s, const uint8_t *seq, const uint8_t *qual,
                      const uint64_t *offsets, size_t n_reads, int k, int min_bq, uint64_t *counts,
                      int n_threads) {
@@ -157,38 +159,83 @@ void orc_count_reads(const orc_set *s, const uint8_t *seq, const uint8_t *qual,
 #else
   n_threads = 1;
 #endif
-#pragma omp parallel num_threads(n_threads)
-  {
-    uint64_t *local = (uint64_t *)calloc(s->n_entries ? s->n_entries : 1, sizeof(uint64_t));
-#pragma omp for schedule(dynamic, 1024)
-    for (long long r = 0; r < (long long)n_reads; r++) {
-      const uint8_t *rs = seq + offsets[r];
-      const uint8_t *rq = qual ? qual + offsets[r] : NULL;
-      size_t len = (size_t)(offsets[r + 1] - offsets[r]);
-      uint64_t fwd = 0, rc = 0;
-      int run = 0;
-      for (size_t i = 0; i < len; i++) {
-        int c = orc_base_code(rs[i]);
-        if (c < 0 || (rq && (int)rq[i] < min_bq)) {
-          run = 0;
-          fwd = rc = 0;
-          continue;
-        }
-        fwd = ((fwd << 2) | (uint64_t)c) & mask;
-        rc = (rc >> 2) | ((uint64_t)(3 - c) << (2 * (k - 1)));
-        if (++run >= k) {
-          uint64_t key = fwd < rc ? fwd : rc;
-          size_t h = orc_hash(key, cap);
-          while (s->slots[h].ent != ORC_NO_ENTRY) {
-            if (s->slots[h].key == key) local[s->slots[h].ent]++;
-            h = (h + 1) & (cap - 1);
+#pragma omp parallel for schedule(dynamic, 1024) num_threads(n_threads)
+  for (long long r = 0; r < (long long)n_reads; r++) {
+    const uint8_t *rs = seq + offsets[r];
+    const uint8_t *rq = qual ? qual + offsets[r] : NULL;
+    size_t len = (size_t)(offsets[r + 1] - offsets[r]);
+    uint64_t fwd = 0, rc = 0;
+    int run = 0;
+    for (size_t i = 0; i < len; i++) {
+      int c = orc_base_code(rs[i]);
+      if (c < 0 || (rq && (int)rq[i] < min_bq)) {
+        run = 0;
+        fwd = rc = 0;
+        continue;
+      }
+      fwd = ((fwd << 2) | (uint64_t)c) & mask;
+      rc = (rc >> 2) | ((uint64_t)(3 - c) << (2 * (k - 1)));
+      if (++run >= k) {
+        uint64_t key = fwd < rc ? fwd : rc;
+        size_t h = orc_hash(key, cap);
+        while (s->slots[h].ent != ORC_NO_ENTRY) {
+          if (s->slots[h].key == key) {
+#pragma omp atomic
+            counts[s->slots[h].ent]++;
           }
+          h = (h + 1) & (cap - 1);
         }
       }
     }
-#pragma omp critical
-    for (size_t e = 0; e < s->n_entries; e++) counts[e] += local[e];
-    free(local);
+  }
+}
+
+/* The same count taken from a PACKED read stream (include/dkb.h: 2-bit bases, 16 per
+ * uint32 word; 1-bit usable flags, 32 per word; one flag-0 separator after every read) -
+ * what the host packer hands to the device.  A flag-0 position resets the window exactly
+ * like an N or a low-quality base does in orc_read_kmers, so for a stream packed from reads
+ * this equals orc_count_reads on those reads (tests/test_oracle.py checks that).  Lets the
+ * full-size parity tests and bench.py check the GPU on the very streams it scanned.
+ * Positions are cut into blocks; a block rolls in from k-1 positions before its start. */
+void orc_count_stream(const orc_set *s, const uint32_t *bases2, const uint32_t *mask1,
+                      uint64_t n_positions, int k, uint64_t *counts, int n_threads) {
+  const uint64_t mask = kmask(k);
+  const size_t cap = s->cap;
+  const uint64_t block = 1u << 20;
+  const long long n_blocks = (long long)((n_positions + block - 1) / block);
+#ifdef _OPENMP
+  if (n_threads < 1) n_threads = omp_get_max_threads();
+#else
+  n_threads = 1;
+#endif
+#pragma omp parallel for schedule(dynamic, 4) num_threads(n_threads)
+  for (long long b = 0; b < n_blocks; b++) {
+    const uint64_t lo = (uint64_t)b * block;
+    const uint64_t hi = lo + block < n_positions ? lo + block : n_positions;
+    uint64_t p = lo >= (uint64_t)(k - 1) ? lo - (uint64_t)(k - 1) : 0; /* roll-in */
+    uint64_t fwd = 0, rc = 0;
+    int run = 0;
+    for (; p < hi; p++) {
+      if (!((mask1[p >> 5] >> (p & 31)) & 1u)) {
+        run = 0;
+        fwd = rc = 0;
+        continue;
+      }
+      const uint64_t c = (bases2[p >> 4] >> (2 * (p & 15))) & 3u;
+      fwd = ((fwd << 2) | c) & mask;
+      rc = (rc >> 2) | ((3 - c) << (2 * (k - 1)));
+      if (++run >= k && p >= lo) { /* the window ENDING at p belongs to this block */
+        uint64_t key = fwd < rc ? fwd : rc;
+        size_t h = orc_hash(key, cap);
+        while (s->slots[h].ent != ORC_NO_ENTRY) {
+          if (s->slots[h].key == key) {
+#pragma omp atomic
+            counts[s->slots[h].ent]++;
+          }
+          h = (h + 1) & (cap - 1);
+        }
+      }
+    }
   }
 }
 

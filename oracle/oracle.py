@@ -44,6 +44,7 @@ def lib():
         L.orc_set_live.argtypes = [C.c_void_p, u8p]
         L.orc_count_reads.argtypes = [C.c_void_p, u8p, u8p, u64p, C.c_size_t, C.c_int, C.c_int,
                                       u64p, C.c_int]
+        L.orc_count_stream.argtypes = [C.c_void_p, u32p, u32p, C.c_uint64, C.c_int, u64p, C.c_int]
         L.orc_variant_stats.argtypes = [C.c_void_p, u32p, u8p, u64p, C.c_size_t, u64p, u64p, u32p]
         L.orc_calls.argtypes = [u64p, u64p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32,
                                 C.c_uint32, u8p]
@@ -110,6 +111,17 @@ class KmerSet:
                               len(offsets) - 1, k, min_bq, _p(counts, u64p), threads)
         return counts
 
+    def count_stream(self, bases2, mask1, n_positions, k, counts=None, threads=0):
+        """Same count from a packed stream (include/dkb.h layout): uint32 arrays."""
+        bases2 = np.ascontiguousarray(bases2).view(np.uint32)
+        mask1 = np.ascontiguousarray(mask1).view(np.uint32)
+        assert len(bases2) * 16 >= n_positions and len(mask1) * 32 >= n_positions
+        if counts is None:
+            counts = np.zeros(self.n, dtype=np.uint64)
+        lib().orc_count_stream(self._h, _p(bases2, u32p), _p(mask1, u32p), int(n_positions), k,
+                               _p(counts, u64p), threads)
+        return counts
+
     def variant_stats(self, counts3, n_variants):
         """counts3: uint64 [3, n_entries] -> hits[nv,2,3], distinct[nv,2,3], n_kmers[nv,2]."""
         counts3 = np.ascontiguousarray(counts3, dtype=np.uint64).reshape(3, self.n)
@@ -120,6 +132,40 @@ class KmerSet:
                                 _p(counts3, u64p), n_variants, _p(hits, u64p), _p(dist, u64p),
                                 _p(nk, u32p))
         return hits, dist, nk
+
+
+def pack_stream(seq, qual, offsets, min_bq=0):
+    """NumPy restatement of the packed read stream of include/dkb.h (bases2, mask1,
+    n_positions): 2-bit codes A=0 C=1 G=2 T=3, flag = usable base, one flag-0 separator
+    position after every read.  Independent of the library's packers (which are checked
+    against it)."""
+    seq = np.ascontiguousarray(seq, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64).astype(np.int64)
+    n_reads = len(offsets) - 1
+    lens = np.diff(offsets)
+    base0 = int(offsets[0]) if n_reads else 0
+    n_bases = int(offsets[-1]) - base0 if n_reads else 0
+    n_pos = n_bases + n_reads
+    code = np.full(256, 255, dtype=np.uint8)
+    for i, ch in enumerate("ACGT"):
+        code[ord(ch)] = i
+        code[ord(ch.lower())] = i
+    c = code[seq[base0:base0 + n_bases]]
+    ok = c != 255
+    if qual is not None:
+        ok &= np.ascontiguousarray(qual, dtype=np.uint8)[base0:base0 + n_bases] >= min_bq
+    # stream position of every base: its index plus the number of reads that ended before it
+    read_of = np.repeat(np.arange(n_reads, dtype=np.int64), lens)
+    pos = np.arange(n_bases, dtype=np.int64) + read_of
+    bw = (n_pos + 63) // 64 * 4
+    mw = (n_pos + 127) // 128 * 4
+    codes = np.zeros(bw * 16, dtype=np.uint64)
+    flags = np.zeros(mw * 32, dtype=np.uint64)
+    codes[pos] = np.where(ok, c, 0)
+    flags[pos] = ok
+    bases2 = (codes.reshape(-1, 16) << (2 * np.arange(16, dtype=np.uint64))).sum(1).astype(np.uint32)
+    mask1 = (flags.reshape(-1, 32) << np.arange(32, dtype=np.uint64)).sum(1).astype(np.uint32)
+    return bases2, mask1, n_pos
 
 
 def calls(hits, distinct, thr):

@@ -254,3 +254,50 @@ def test_rust_sys_crate_declares_every_symbol():
     rs_stats = re.search(r"pub struct DkbStats \{(.*?)\n\}", rs, re.S).group(1)
     rs_fields = re.findall(r"pub (\w+):", rs_stats)
     assert c_fields == rs_fields, (c_fields, rs_fields)
+
+
+def test_rust_safe_crate_uses_only_declared_symbols():
+    """bindings/rust/denovo-kmer-gpu (RAII Counter, Result errors, pinned BatchPacker, the
+    INTEGRATION.md loop as examples/trio.rs) cannot be compiled here; check that every
+    sys::dkb_* call it makes exists in the -sys crate and passes the declared number of
+    arguments, and that every safe method the example uses exists."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sysrs = open(os.path.join(root, "bindings", "rust", "denovo-kmer-gpu-sys", "src", "lib.rs")).read()
+    safe = open(os.path.join(root, "bindings", "rust", "denovo-kmer-gpu", "src", "lib.rs")).read()
+    example = open(os.path.join(root, "bindings", "rust", "denovo-kmer-gpu", "examples", "trio.rs")).read()
+    arity = {}
+    for name, args in re.findall(r"pub fn (dkb_[a-z_]+)\((.*?)\)\s*(?:->|;)", sysrs, re.S):
+        arity[name] = 0 if not args.strip() else args.count(":")
+
+    def call_args(text, start):
+        depth, i, n, seen = 0, start, 0, False
+        while True:
+            ch = text[i]
+            if ch in "([{":
+                depth += 1
+            elif ch in ")]}":
+                depth -= 1
+                if depth == 0:
+                    return n + (1 if seen else 0)
+            elif ch == "," and depth == 1:
+                n += 1
+                seen = False
+            elif not ch.isspace() and depth >= 1 and not (depth == 1 and ch == "("):
+                seen = True
+            i += 1
+
+    used = set()
+    for m in re.finditer(r"sys::(dkb_[a-z_]+)\(", safe):
+        name = m.group(1)
+        used.add(name)
+        assert name in arity, f"{name} is not declared in the -sys crate"
+        assert call_args(safe, m.end() - 1) == arity[name], name
+    assert {"dkb_ctx_create", "dkb_ctx_destroy", "dkb_table_build", "dkb_batch_submit", "dkb_pack_reads",
+            "dkb_host_alloc", "dkb_finalise", "dkb_results_fetch", "dkb_comm_init",
+            "dkb_reduce_push"} <= used
+    methods = set(re.findall(r"pub fn (\w+)", safe))
+    for m in re.findall(r"(?:kc|packer)\.(\w+)\(", example):
+        assert m in methods, f"examples/trio.rs calls {m}() which the safe crate does not define"
+    assert "impl Drop for Counter" in safe and "Result<" in safe

@@ -133,3 +133,37 @@ def test_golden_fixtures(orc):
         hits, dist, nk = ks.variant_stats(counts, len(case["variants"]))
         assert hits.tolist() == case["hits"] and dist.tolist() == case["distinct"]
         assert orc.calls(hits, dist, case["thresholds"]).tolist() == case["calls"]
+
+
+def test_count_stream_equals_count_reads(orc):
+    """The packed-stream form of the count (what the full-size GPU parity tests and bench.py
+    use as the checker) equals the per-read form on ragged reads with N and low-quality
+    bases, for several k and thread counts; block boundaries (2^20 positions) are crossed."""
+    from denovo_kmer_b200 import synth
+    for k, seed in ((31, 5), (15, 6), (8, 7)):
+        trio = synth.make_trio_host(60_000, 40, 25, k, seed=seed, indel_frac=0.3, ragged=(k == 15),
+                                    n_rate=0.003, lowq_frac=0.05)
+        keys, var, al, _, _ = orc.variant_entries(trio.variant_tuples(), k)
+        ks = orc.KmerSet(keys, var, al)
+        for smp in range(3):
+            seq, qual, off = trio.reads[smp]
+            want = ks.count_reads(seq, qual, off, k, 20)
+            b2, m1, n_pos = orc.pack_stream(seq, qual, off, 20)
+            assert n_pos == len(seq) + len(off) - 1
+            if k != 15:
+                assert n_pos > (1 << 20)
+            for threads in (1, 3):
+                got = ks.count_stream(b2, m1, n_pos, k, threads=threads)
+                assert np.array_equal(got, want), (k, smp, threads)
+            assert want.sum() > 0
+
+
+def test_pack_stream_known_answer(orc):
+    # reads "ACGN" (q 30,30,5,30) and "TT": positions A C G N | T T |  -> 8 positions
+    seq = np.frombuffer(b"ACGNTT", dtype=np.uint8)
+    qual = np.array([30, 30, 5, 30, 30, 30], dtype=np.uint8)
+    off = np.array([0, 4, 6], dtype=np.uint64)
+    b2, m1, n_pos = orc.pack_stream(seq, qual, off, 20)
+    assert n_pos == 8 and len(b2) == 4 and len(m1) == 4
+    # codes: A=0 C=1 (G masked -> 0) (N -> 0) sep T=3 T=3 sep ; flags 1 1 0 0 0 1 1 0
+    assert int(b2[0]) == (1 << 2) | (3 << 10) | (3 << 12) and int(m1[0]) == 0b01100011
