@@ -817,6 +817,26 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
     CU(cudaStreamSynchronize(st));
     ctx->bloom_bits_set = h_stats[0];
     ctx->n_live = (size_t)h_stats[1];
+    // Optional (DKB_L2_PERSIST_MB=n): set n MB of L2 aside for persisting lines and mark the
+    // L2 filter as such for everything launched on the scan stream.
+    if (const char *e = getenv("DKB_L2_PERSIST_MB")) {
+      const size_t want = (size_t)atol(e) << 20;
+      cudaStreamAttrValue av;
+      memset(&av, 0, sizeof(av));
+      if (want && ctx->gf) {
+        CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+        size_t bytes = (size_t)ctx->bloom_words * 4;
+        int max_win = 0;
+        CU(cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device));
+        if (bytes > (size_t)max_win) bytes = (size_t)max_win;
+        av.accessPolicyWindow.base_ptr = ctx->d_bloom;
+        av.accessPolicyWindow.num_bytes = bytes;
+        av.accessPolicyWindow.hitRatio = bytes <= want ? 1.0f : (float)want / (float)bytes;
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      }
+      CU(cudaStreamSetAttribute(ctx->s_scan, cudaStreamAttributeAccessPolicyWindow, &av));
+    }
     return DKB_OK;
   }();
   cleanup();

@@ -23,6 +23,26 @@ def test_reference_arm_json_contract():
     assert d["e2e"] == {"value": d["value"], "unit": "bases/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["vs_baseline"] is None
+    assert d["config"]["step_fraction"] == 1.0  # small workloads run the whole step
+
+
+def test_reference_arm_does_not_load_the_product(tmp_path):
+    """The reference arm must not map libdkb.so (nor import the package that binds it): its
+    numbers are the oracle's alone."""
+    code = (
+        "import sys, runpy\n"
+        "sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0', '--genome-mb', '1', '--variants', '50']\n"
+        "try:\n"
+        "    runpy.run_path(%r, run_name='__main__')\n"
+        "except SystemExit:\n"
+        "    pass\n"
+        "maps = open('/proc/self/maps').read()\n"
+        "assert 'libdkb' not in maps, 'libdkb.so is mapped'\n"
+        "assert 'libdnk_oracle' in maps\n"
+        "assert not any(m == 'denovo_kmer_b200' or m.startswith('denovo_kmer_b200.') for m in sys.modules), 'package imported'\n"
+        "sys.stderr.write('CLEAN\\n')\n" % os.path.join(ROOT, "bench.py"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "CLEAN" in out.stderr, out.stderr[-2000:]
 
 
 def test_reference_arm_other_ranks_exit_quietly():

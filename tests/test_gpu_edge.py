@@ -247,3 +247,98 @@ def test_device_packer_matches_host_packer(dkb, orc, ragged):
         kc.submit_reads(seq, None, off, 0, 99)
         got = kc.entry_counts()[0]
     assert np.array_equal(got.astype(np.uint64), ks.count_reads(seq, None, off, k, 0))
+
+
+def test_rebuild_flips_the_prefilter_within_one_context(dkb, orc, monkeypatch):
+    """The dynamic shared-memory size of an L2-filter kernel follows the pre-filter every
+    table build chooses.  Same kernel (stride, bits), pre-filter off -> on -> off inside one
+    context, and a second context with the other choice alongside: every launch must get the
+    size it needs and every result must equal the oracle's."""
+    trio = synth.make_trio_host(60_000, 10, 12, 31, seed=61)
+    ent = dkb.variant_kmers(trio.variant_tuples(), 31)
+    ks = orc.KmerSet(ent.keys, ent.variant, ent.allele)
+    want = ks.count_reads(*trio.reads[0], 31, 20)
+    st = dkb.pack_reads(*trio.reads[0], 20)
+
+    def run(kc, words):
+        monkeypatch.setenv("DKB_PREFILTER_WORDS", str(words))
+        kc.set_tuning(15, 16, 2, 2)
+        kc.build_table(ent)
+        assert kc.stats()["prefilter_words"] == words
+        kc.submit(st, 0)
+        assert np.array_equal(kc.entry_counts()[0].astype(np.uint64), want), words
+
+    with dkb.KmerCounter(31) as k1, dkb.KmerCounter(31) as k2:
+        for words in (0, 35584, 0, 51712, 4096):
+            run(k1, words)
+            run(k2, 35584 if words == 0 else 0)
+            k1.reset_counts()
+            k1.submit(st, 0)  # k1's kernel again after k2 changed the function's attributes
+            assert np.array_equal(k1.entry_counts()[0].astype(np.uint64), want), words
+    assert want.sum() > 0
+
+
+@pytest.mark.parametrize("tuning", [None, (14, 4, 2, 1), (15, 16, 2, 1), (15, 16, 2, 2), (15, 8, 1, 2), (15, 1, 2, 1)])
+def test_one_launch_for_a_trio_equals_three_launches(dkb, orc, tuning):
+    """dkb_batch_submit_device_multi: the three samples' streams (different lengths, one of them
+    empty in a second round) scanned by ONE launch give the counters of three launches."""
+    import torch
+    dev = torch.device("cuda:0")
+    trio = synth.make_trio_host(150_000, 12, 30, 31, seed=71, indel_frac=0.3)
+    ent = dkb.variant_kmers(trio.variant_tuples(), 31)
+    ks = orc.KmerSet(ent.keys, ent.variant, ent.allele)
+    want = np.zeros((3, len(ent)), dtype=np.uint64)
+    dstreams = []
+    for smp in range(3):
+        seq, qual, off = trio.reads[smp]
+        n = (len(off) - 1) * (smp + 1) // 3          # three different lengths
+        off = off[:n + 1]
+        ks.count_reads(seq, qual, off, 31, 20, counts=want[smp])
+        st = dkb.pack_reads(seq[:int(off[-1])], qual[:int(off[-1])], off, 20)
+        dstreams.append((torch.from_numpy(st.bases2.view(np.int32)).to(dev),
+                         torch.from_numpy(st.mask1.view(np.int32)).to(dev), st.n_positions))
+    with dkb.KmerCounter(31, tuning=tuning) as kc:
+        kc.build_table(ent)
+        kc.submit_device_multi([(b.data_ptr(), m.data_ptr(), n, s) for s, (b, m, n) in enumerate(dstreams)])
+        assert kc.stats()["scan_launches"] == 1
+        assert np.array_equal(kc.entry_counts().astype(np.uint64), want), tuning
+        # same stream twice into one sample, an empty batch in between, sample order reversed
+        kc.reset_counts()
+        b, m, n = dstreams[1]
+        kc.submit_device_multi([(b.data_ptr(), m.data_ptr(), n, 2), (b.data_ptr(), m.data_ptr(), 0, 1),
+                                (b.data_ptr(), m.data_ptr(), n, 2), (dstreams[0][0].data_ptr(), dstreams[0][1].data_ptr(), dstreams[0][2], 0)])
+        got = kc.entry_counts().astype(np.uint64)
+        assert np.array_equal(got[2], 2 * want[1]) and np.array_equal(got[0], want[0]) and got[1].sum() == 0
+        with pytest.raises(dkb.DkbError):
+            kc.submit_device_multi([(b.data_ptr(), m.data_ptr(), n, 0)] * 5)
+    assert want.sum() > 0
+
+
+def test_padding_bits_beyond_the_stream_are_ignored(dkb, orc):
+    """dkb_batch_submit_device takes caller-owned buffers: flag bits at positions >= n_positions
+    (the padding of the last words) must not produce counts, whatever they hold."""
+    import torch
+    dev = torch.device("cuda:0")
+    k = 31
+    trio = synth.make_trio_host(40_000, 10, 10, k, seed=81, n_rate=0.0, lowq_frac=0.0, err_rate=0.0)
+    ent = dkb.variant_kmers(trio.variant_tuples(), k)
+    ks = orc.KmerSet(ent.keys, ent.variant, ent.allele)
+    seq, qual, off = trio.reads[0]
+    full = dkb.pack_reads(seq, qual, off, 20)
+    for cut_reads in (len(off) - 1 - 1, (len(off) - 1) // 2):
+        # scan only the first cut_reads reads, minus a few positions so the cut falls inside a
+        # read: everything after the cut in the buffers is real, valid sequence = worst-case padding
+        n_pos = cut_reads * 151 - 37
+        want = np.zeros(len(ent), dtype=np.uint64)
+        ks.count_reads(seq, qual, off[:cut_reads], k, 20, counts=want)   # whole reads before the cut one
+        a = int(off[cut_reads - 1])
+        tail = np.array([0, 151 - 37], dtype=np.uint64)
+        ks.count_reads(seq[a:a + 150], qual[a:a + 150], tail, k, 20, counts=want)  # the cut read's first 114 bases
+        b = torch.from_numpy(full.bases2.view(np.int32)).to(dev)
+        m = torch.from_numpy(full.mask1.view(np.int32)).to(dev)
+        for tuning in (None, (15, 16, 2, 2), (14, 4, 2, 1), (15, 1, 1, 1)):
+            with dkb.KmerCounter(k, tuning=tuning) as kc:
+                kc.build_table(ent)
+                kc.submit_device(b.data_ptr(), m.data_ptr(), n_pos, 0)
+                assert np.array_equal(kc.entry_counts()[0].astype(np.uint64), want), (cut_reads, tuning)
+    assert want.sum() > 0
