@@ -452,6 +452,23 @@ def run_ours(a):
             kc.counts_allreduce()  # N>1: ncclAllReduce on the scan stream; no-op on one GPU
             return kc.finalise(THRESHOLDS)  # kernel 3 + D2H of hits/distinct/n_kmers/calls
 
+        # the box's H2D ceiling for this job: every rank copies its pinned batches to the device
+        # at once, nothing else running (torch copy = cudaMemcpyAsync; not the product path)
+        dst = torch.empty(max(h[0].size for h in host), dtype=torch.int32, device=dev)
+        job.barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            for (hb, hm, _) in host:
+                dst[: hb.size].copy_(torch.from_numpy(hb.view(np.int32)), non_blocking=True)
+                dst[: hm.size].copy_(torch.from_numpy(hm.view(np.int32)), non_blocking=True)
+        torch.cuda.synchronize()
+        ceil_rate = torch.tensor([2 * (job.stream_bytes + job.mask_bytes) / (time.perf_counter() - t0) / 1e9],
+                                 dtype=torch.float64, device=dev)
+        ceils = [ceil_rate.clone() for _ in range(world)]
+        if world > 1:
+            tdist.all_gather(ceils, ceil_rate)
+        del dst
+
         e2e_step()
         job.barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -476,8 +493,58 @@ def run_ours(a):
                "h2d_bytes_per_step": int(job.stream_bytes + job.mask_bytes), "d2h_bytes_per_step": int(d2h),
                "steps": a.e2e_steps, "counts_equal_device_resident_run": same,
                "h2d_gbs_per_rank": [round(float(r.item()), 2) for r in rates],
+               "h2d_ceiling_gbs_per_rank": [round(float(r.item()), 2) for r in ceils],
                "staging": f"dkb_host_alloc (cudaHostAlloc on the GPU's NUMA node; rank 0: node {job.numa_node})"}
         del host
+
+    # ---- the feeders (f1), rank 0 at N = 1: host packer rate, and an end-to-end leg through the
+    # DEVICE packer (decoded ASCII reads + quality bytes over PCIe, no per-base host work) ----
+    feeders = None
+    if rank == 0 and world == 1 and not a.no_e2e:
+        import denovo_kmer_b200 as dkb
+        from denovo_kmer_b200 import synth
+        n_r = 524_288
+        g = job.genome[: min(len(job.genome), 8_000_000)]
+        raw = [synth.sample_reads([g, g], n_r, READ_LEN, 700 + s) for s in range(3)]
+        nb = n_r * READ_LEN
+
+        def pack_rate(threads):
+            os.environ["DKB_PACK_THREADS"] = str(threads)
+            seq, qual, off = raw[0]
+            dkb.pack_reads(seq, qual, off, 20)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                dkb.pack_reads(seq, qual, off, 20)
+            return 3 * nb / (time.perf_counter() - t0)
+
+        cores = min(os.cpu_count() or 1, 32)
+        r1, rn = pack_rate(1), pack_rate(cores)
+        os.environ.pop("DKB_PACK_THREADS", None)
+
+        pinned = []  # the BAM layer's decoded records, in page-locked buffers next to the GPU
+        for (seq, qual, off) in raw:
+            ps = kc.host_alloc((len(seq) + 3) // 4).view(np.uint8)[: len(seq)]
+            pq = kc.host_alloc((len(qual) + 3) // 4).view(np.uint8)[: len(qual)]
+            ps[:], pq[:] = seq, qual
+            pinned.append((ps, pq, off))
+
+        def reads_step():
+            kc.reset_counts()
+            for s, (seq, qual, off) in enumerate(pinned):
+                kc.submit_reads(seq, qual, off, s, 20)
+            return kc.finalise(THRESHOLDS)
+
+        reads_step()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            reads_step()
+        el = time.perf_counter() - t0
+        feeders = {"host_packer_bases_per_s": {"1_thread": r1, f"{cores}_threads": rn},
+                   "device_packer_e2e": {"value": 5 * 3 * nb / el, "unit": UNIT,
+                                         "h2d_bytes_per_base": 2.0 + 8.0 / READ_LEN,
+                                         "what": "dkb_batch_submit_reads: pinned ASCII reads + quality bytes -> H2D -> "
+                                                 "k_pack -> k_scan -> finalise + D2H, 3 x 524 288 reads per step"}}
+        del raw
 
     out = None
     if rank == 0:
@@ -501,6 +568,7 @@ def run_ours(a):
             "roofline": roof,
             "cpu_baseline": cpu,
             "e2e": e2e,
+            "feeders": feeders,
             "checks": {"reduced_equals_sum_of_ranks": sum_ok,
                        "cpu_oracle_matches_gpu": cpu["matches_gpu"] if cpu else None,
                        "e2e_equals_device_resident": e2e["counts_equal_device_resident_run"] if e2e else None},

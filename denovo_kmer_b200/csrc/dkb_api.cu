@@ -47,7 +47,8 @@ struct dkb_ctx {
   uint4 *d_tslots = nullptr;
   uint32_t table_slots = 0;
   // seeds
-  uint4 *d_sslots = nullptr;  // seed table: 32-byte slots (seed + record), 2 x uint4 each
+  uint4 *d_sslots = nullptr;  // seed table: 64-byte slots (seed + two records), 4 x uint4 each
+  bool canon = false;         // seeds keyed by their strand-canonical form
   uint32_t seed_slots = 0;
   uint32_t n_seeds = 0;
   uint32_t *d_bloom = nullptr, *d_pre = nullptr;
@@ -195,6 +196,7 @@ double tile_cost(double n_entries, bool hints, int k, int s, int D, int NH, bool
   // both strands; ref/alt haplotypes share the seeds that avoid the variant base (x0.7)
   double seeds = n_haps * 2.0 * 0.7 * ladder_seeds_per_strand(k, s, D);
   if (!hints) seeds *= 2.3;  // min-hash rule: ~2/(w+1) density instead of 1/w
+  if (canon_for_mode(gf ? 1 : 0)) seeds *= 0.5;  // both strands share their (canonical) seeds
   if (seeds_out) *seeds_out = seeds;
   const double bits = 32.0 * (gf ? l2_filter_words(seeds) : (double)BLOOM_WORDS);
   const double dens = 1.0 - exp(-NH * seeds / bits);
@@ -310,21 +312,21 @@ typedef void (*scan_fn)(const ScanParams);
 // The scan kernel's instantiations are compiled one stride per translation unit
 // (dkb_scan_inst.cu with -DDKB_INST_D=...), in parallel; each exports its picker.
 namespace dkb {
-scan_fn pick_scan_d1(int NH, bool gf, bool prof);
-scan_fn pick_scan_d2(int NH, bool gf, bool prof);
-scan_fn pick_scan_d4(int NH, bool gf, bool prof);
-scan_fn pick_scan_d8(int NH, bool gf, bool prof);
-scan_fn pick_scan_d16(int NH, bool gf, bool prof);
+scan_fn pick_scan_d1(int NH, int fm, bool prof);
+scan_fn pick_scan_d2(int NH, int fm, bool prof);
+scan_fn pick_scan_d4(int NH, int fm, bool prof);
+scan_fn pick_scan_d8(int NH, int fm, bool prof);
+scan_fn pick_scan_d16(int NH, int fm, bool prof);
 }  // namespace dkb
 
 namespace {
-scan_fn pick_scan(int D, int NH, bool gf, bool prof) {
+scan_fn pick_scan(int D, int NH, int fm, bool prof) {
   switch (D) {
-    case 1: return pick_scan_d1(NH, gf, prof);
-    case 2: return pick_scan_d2(NH, gf, prof);
-    case 4: return pick_scan_d4(NH, gf, prof);
-    case 8: return pick_scan_d8(NH, gf, prof);
-    case 16: return pick_scan_d16(NH, gf, prof);
+    case 1: return pick_scan_d1(NH, fm, prof);
+    case 2: return pick_scan_d2(NH, fm, prof);
+    case 4: return pick_scan_d4(NH, fm, prof);
+    case 8: return pick_scan_d8(NH, fm, prof);
+    case 16: return pick_scan_d16(NH, fm, prof);
   }
   return nullptr;
 }
@@ -364,15 +366,17 @@ int launch_scan(dkb_ctx *ctx, int n_seg, const uint32_t *const *d_bases, const u
   P.kt = key_table(ctx);
   P.seed_mult = SEED_MULT << (32 - 2 * ctx->s);
   P.seed_mask = (1u << (2 * ctx->s)) - 1;
+  P.cshift = 32 - 2 * ctx->s;
   P.four = 4;
   for (int i = 0; i < 32; i++) P.pw[i] = 1u << i;
   P.filter_words = BLOOM_WORDS;
   P.k = ctx->k;
   P.s = ctx->s;
   P.prof = ctx->d_prof;
-  scan_fn fn = pick_scan(ctx->D, ctx->NH, ctx->gf, ctx->prof);
+  scan_fn fn = pick_scan(ctx->D, ctx->NH, ctx->gf ? (ctx->pre_words ? 2 : 1) : 0, ctx->prof);
   if (!fn) return fail(ctx, DKB_EINVAL, "no scan kernel for this tuning");
-  const size_t smem_bytes = ctx->gf ? SCAN_SMEM_BYTES_GF + (size_t)ctx->pre_words * 4 : SCAN_SMEM_BYTES;
+  size_t smem_bytes = ctx->gf ? SCAN_SMEM_BYTES_GF + (size_t)ctx->pre_words * 4 : SCAN_SMEM_BYTES;
+  if (ctx->D >= 8) smem_bytes += SCAN_TMA_BYTES;  // TMA builds: the per-warp stream ring of the macro path
   {
     std::lock_guard<std::mutex> lk(g_smem_mu);
     auto it = g_smem_set.find({ctx->device, (const void *)fn});
@@ -762,6 +766,9 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
     B.win_index = d_wi; B.win_count = d_wc; B.n = (uint32_t)n;
     B.kt = key_table(ctx); B.slot_of = d_slot_of; B.dead = ctx->d_dead;
     B.k = ctx->k; B.s = ctx->s; B.D = ctx->D;
+    // (whether the L2 mode runs behind a pre-filter does not matter here: both are mode > 0)
+    ctx->canon = canon_for_mode(ctx->gf ? 1 : 0);
+    B.canon = ctx->canon;
     const uint32_t seed_mult = SEED_MULT << (32 - 2 * ctx->s);
     const int TB = 256;
     const uint32_t g1 = (uint32_t)((n + TB - 1) / TB), g2 = (uint32_t)((2 * n + TB - 1) / TB);
@@ -777,17 +784,18 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
     CU(cudaMemcpyAsync(&n_seeds, d_nseeds, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     ctx->n_seeds = n_seeds;
-    // Seed table: 32-byte slots (seed + record), half full, any size.  Only occupied slots are
-    // ever touched by true hits, so the hot set is 32 B per seed; an absent seed (a filter
-    // false positive) lands on a slot marked ST_MOVED_BIT - a second load - about one time in 8.
+    // Seed table: 64-byte slots (seed + a 32-byte record per read orientation), half full, any
+    // size.  Only occupied slots are ever touched by true hits, so the hot set is 32 B per seed
+    // and orientation; an absent seed (a filter false positive) lands on a slot marked
+    // ST_MOVED_BIT - a second load - about one time in 8.
     double per_seed = 2.0;
     if (const char *e = getenv("DKB_SEED_SLOTS_PER_SEED")) per_seed = atof(e) >= 1.1 ? atof(e) : per_seed;
     const double want_slots = per_seed * n_seeds + 64;
     if (want_slots >= 4294967295.0) return fail(ctx, DKB_EINVAL, "too many seeds for the seed table");
     ctx->seed_slots = (uint32_t)want_slots;
-    CU(cudaMalloc(&ctx->d_sslots, (size_t)ctx->seed_slots * 32));
-    CU(cudaMalloc(&d_cov, (size_t)ctx->seed_slots * 12));
-    CU(cudaMemsetAsync(d_cov, 0, (size_t)ctx->seed_slots * 12, st));
+    CU(cudaMalloc(&ctx->d_sslots, (size_t)ctx->seed_slots * 64));
+    CU(cudaMalloc(&d_cov, (size_t)ctx->seed_slots * 24));
+    CU(cudaMemsetAsync(d_cov, 0, (size_t)ctx->seed_slots * 24, st));
     ctx->bloom_words = ctx->gf ? l2_filter_words((double)n_seeds) / 4 * 4 : (uint32_t)BLOOM_WORDS;
     CU(cudaMalloc(&ctx->d_bloom, (size_t)ctx->bloom_words * 4));
     CU(cudaMemsetAsync(ctx->d_bloom, 0, (size_t)ctx->bloom_words * 4, st));
@@ -797,7 +805,7 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
       CU(cudaMemsetAsync(ctx->d_pre, 0, (size_t)ctx->pre_words * 4, st));
     }
     const SeedTable T = seed_table(ctx);
-    k_init_slots<<<(uint32_t)((2 * (size_t)ctx->seed_slots + TB - 1) / TB), TB, 0, st>>>(T);
+    k_init_slots<<<(uint32_t)((4 * (size_t)ctx->seed_slots + TB - 1) / TB), TB, 0, st>>>(T);
     if (n) {
       k_assign_seeds<<<g2, TB, 0, st>>>(B, ASSIGN_INSERT, nullptr, 0, nullptr, T, nullptr,
                                         ctx->d_bloom, ctx->bloom_words, ctx->d_pre, ctx->pre_words,
@@ -805,7 +813,7 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
       k_assign_seeds<<<g2, TB, 0, st>>>(B, ASSIGN_RECORD, nullptr, 0, nullptr, T, d_cov,
                                         ctx->d_bloom, ctx->bloom_words, ctx->d_pre, ctx->pre_words,
                                         seed_mult, ctx->NH);
-      k_finish_records<<<(ctx->seed_slots + TB - 1) / TB, TB, 0, st>>>(T, d_cov);
+      k_finish_records<<<(uint32_t)((2 * (size_t)ctx->seed_slots + TB - 1) / TB), TB, 0, st>>>(T, d_cov);
     }
     // build statistics, counted on the device (the filter can be 16 MB)
     CU(cudaMalloc(&d_stats, 16));

@@ -21,6 +21,7 @@ struct BuildParams {
   uint32_t *slot_of;  // [n] slot claimed by each entry
   uint8_t *dead;      // [n]
   int k, s, D;
+  int canon;  // seeds are keyed by min(s-mer, its reverse complement)
 };
 
 // Claim one free slot for every entry: home bucket first, then the following
@@ -75,9 +76,9 @@ __global__ void k_apply_dead(const BuildParams B) {
   if (B.dead[i]) B.kt.slots[B.slot_of[i]].z = ENTRY_DEAD;
 }
 
-// Word w of seed-table slot `slot` (8 words per slot; layout in dkb_device.cuh).
-__device__ __forceinline__ uint32_t *slot_word(const SeedTable &T, uint32_t slot, int w) {
-  return reinterpret_cast<uint32_t *>(T.slots) + 8 * (size_t)slot + w;
+// Word w of half h (0, 1) of seed-table slot `slot` (layout in dkb_device.cuh).
+__device__ __forceinline__ uint32_t *slot_word(const SeedTable &T, uint32_t slot, int w, int h = 0) {
+  return reinterpret_cast<uint32_t *>(T.slots) + 16 * (size_t)slot + 8 * h + w;
 }
 
 // Insert a seed into the seed table: the home slot, else the first free slot after it,
@@ -126,19 +127,19 @@ __device__ __forceinline__ void record_add(uint32_t *rec, uint32_t *cov, int j, 
   }
 }
 
-// Every slot free, its record in the (empty) working form.
+// Every slot free, both its records in the (empty) working form.
 __global__ void k_init_slots(const SeedTable T) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per uint4
-  if (i >= 2 * (size_t)T.n_slots) return;
+  if (i >= 4 * (size_t)T.n_slots) return;
   T.slots[i] = (i & 1) ? make_uint4(0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu)
                        : make_uint4(ST_EMPTY, 0u, 0u, 0u);
 }
 
 __global__ void k_finish_records(const SeedTable T, const uint32_t *cov) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= T.n_slots) return;
-  uint32_t *r = slot_word(T, i, 0);
-  if (r[0] & ST_FREE_BIT) return;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per half
+  if (i >= 2 * (size_t)T.n_slots) return;
+  if (*slot_word(T, (uint32_t)(i >> 1), 0) & ST_FREE_BIT) return;
+  uint32_t *r = slot_word(T, (uint32_t)(i >> 1), 0, (int)(i & 1));
 #pragma unroll
   for (int w = 0; w < 3; w++) {
     const uint32_t d = r[2 + w] ^ r[5 + w];               // bases on which the windows disagree
@@ -241,7 +242,10 @@ __global__ void k_assign_seeds(const BuildParams B, int pass, uint32_t *set, uin
         }
       }
     }
-    const uint32_t seed = (uint32_t)(v >> (2 * j)) & smask;
+    uint32_t seed = (uint32_t)(v >> (2 * j)) & smask, flip = 0;
+    // canonical seeds: the seed is stored once for both strands; reads that show this
+    // orientation of it are served by half `flip` of its slot
+    if (B.canon) seed = seed_canon(seed, 32 - 2 * s, flip);
     if (pass == ASSIGN_COUNT) {
       seedset_insert(set, set_mask, seed, n_seeds);
     } else if (pass == ASSIGN_INSERT) {
@@ -249,13 +253,13 @@ __global__ void k_assign_seeds(const BuildParams B, int pass, uint32_t *set, uin
       seedtab_insert(T, seed);
       uint32_t h = seed * seed_mult;
       if (pre_words) {  // one-bit pre-filter; the main filter behind it uses an independent hash
-        atomicOr(pre + bloom_word(h, pre_words), 1u << ((uint32_t)((uint64_t)h * pre_words) >> 27));
+        atomicOr(pre + bloom_word(h, pre_words), 1u << (seed & 31));
         h *= PRE_REHASH;
       }
       atomicOr(bloom + bloom_word(h, bloom_words), bloom_bits(seed, h, bloom_words, n_hashes));
     } else {
       const uint32_t slot = seedtab_find(T, seed);
-      record_add(slot_word(T, slot, 0), cov + (size_t)slot * 3, j, v, k, E);
+      record_add(slot_word(T, slot, 0, (int)flip), cov + ((size_t)slot * 2 + flip) * 3, j, v, k, E);
     }
   }
   if (pass == ASSIGN_INSERT) atomicOr(&B.kt.slots[B.slot_of[i]].w, offs);

@@ -14,7 +14,11 @@ constexpr int SCAN_WARPS = SCAN_THREADS / 32;
 constexpr int CHUNK = 64;                  // stream positions per lane per tile (4 words)
 constexpr int WTILE = 32 * CHUNK;          // positions per warp tile (512 B of bases)
 constexpr int WTILE_WORDS = WTILE / 16;    // 128 uint32 words of bases per warp tile
-constexpr int BLOOM_WORDS = 51712;         // 202 KB seed filter resident in shared memory
+#ifndef DKB_STREAM_LD
+#define DKB_STREAM_LD 1
+#endif
+// 202 KB seed filter resident in shared memory (136 KB in TMA builds, whose stream ring needs 66 KB)
+constexpr int BLOOM_WORDS = DKB_STREAM_LD == 2 ? 34816 : 51712;
 constexpr int HL_CAP = 128;                // per-warp list of filter-hit ids of one tile
 constexpr int CQ_CAP = 64;                 // per-warp ring of verified seeds
 constexpr size_t SCAN_LISTS_BYTES = (size_t)SCAN_WARPS * CQ_CAP * 8 + (size_t)SCAN_WARPS * HL_CAP * 2;
@@ -23,6 +27,23 @@ constexpr size_t SCAN_SMEM_BYTES = (size_t)BLOOM_WORDS * 4 + SCAN_LISTS_BYTES;
 // lines are what outstanding global loads are tracked in (a 30 KB L1 caps an SM at ~0.3
 // random loads per clock against 1.0 with a large one: scripts/micro/l2_gather.cu).
 constexpr size_t SCAN_SMEM_BYTES_GF = SCAN_LISTS_BYTES;
+
+// DKB_STREAM_LD: how the macro path (strides 8, 16) reads the base stream.
+//   0  read-only loads at normal L2 priority        1  evict-first loads (default)
+//   2  TMA: one lane per warp issues a 1-D bulk copy (cp.async.bulk) of each group of
+//      sub-tiles into a per-warp shared-memory ring, completion on an mbarrier; the stream
+//      never touches the LSU/L1 path the filter lookups need
+#ifndef DKB_STREAM_LD
+#define DKB_STREAM_LD 1
+#endif
+#ifndef DKB_TMA_STAGES
+#define DKB_TMA_STAGES 2
+#endif
+constexpr int MACRO_GS = 2;  // sub-tiles per group of the macro path
+constexpr int TMA_NST = DKB_TMA_STAGES;
+constexpr uint32_t TMA_STAGE_BYTES = MACRO_GS * 512 + 16;  // + the 16 bytes that hold the halo word
+constexpr size_t SCAN_TMA_BYTES =
+    DKB_STREAM_LD == 2 ? (size_t)SCAN_WARPS * TMA_NST * (TMA_STAGE_BYTES + 8) : 0;  // ring + mbarriers
 
 constexpr int MAX_SEED_LEN = 15;             // 30 bits: leaves SEED_EMPTY outside the seed space
 constexpr uint32_t SEED_MULT = 0x9E3779B1u;  // odd multiplier of the filter hash
@@ -77,6 +98,29 @@ __host__ __device__ __forceinline__ uint32_t bloom_bits(uint32_t seed, uint32_t 
 
 __host__ __device__ __forceinline__ uint64_t kmer_mask(int k) { return (1ull << (2 * k)) - 1; }
 
+// DKB_CANON: which filter modes key their seeds by the strand-canonical form of the s-mer,
+// min(s-mer, its reverse complement): 0 none, 1 the L2 filter modes (default), 2 all.  Both
+// orientations of a haplotype then share their seeds: half the seeds in the filters and the
+// seed table, for ~7 more instructions per lookup.
+#ifndef DKB_CANON
+#define DKB_CANON 1
+#endif
+__host__ __device__ constexpr bool canon_for_mode(int fm) { return DKB_CANON == 2 || (DKB_CANON == 1 && fm > 0); }
+
+// Reverse complement of an s-mer held in the low 2s bits (stream order either way: first base
+// least significant), cshift = 32 - 2s; x must be masked to its 2s bits.
+__device__ __forceinline__ uint32_t seed_revcomp(uint32_t x, uint32_t cshift) {
+  uint32_t r = __brev(x);  // bases reversed (now in the top 2s bits), the two bits of each base swapped
+  r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);  // swap them back
+  return ~r >> cshift;     // complement and realign (the ones below the s-mer are shifted out)
+}
+// Canonical seed and whether the s-mer had to be flipped to get it.
+__device__ __forceinline__ uint32_t seed_canon(uint32_t x, uint32_t cshift, uint32_t &flip) {
+  const uint32_t r = seed_revcomp(x, cshift);
+  flip = r < x;
+  return r < x ? r : x;
+}
+
 // Reverse the order of the k bases of a 2k-bit value (an involution).  Turns
 // a key (first base most significant) into stream order (first base least
 // significant) and back.
@@ -118,10 +162,13 @@ __device__ __forceinline__ uint64_t ldg_u64_hint(const void *ptr, uint64_t pol) 
 }
 
 // ---- the two lookup structures (both in L2) -----------------------------------
-// Seed table: open addressing, linear probing, 32-byte slots = ONE L2 sector that holds the
-// seed AND its record, so a verified seed costs no further dependent load:
-//   word 0   bits 0..29 the seed, bit 30 = slot is free, bit 31 = some seed whose home is
-//            this slot lives further along (a miss must walk on); see ST_*
+// Seed table: open addressing, linear probing, 64-byte slots of two 32-byte HALVES (one L2
+// sector each).  A half holds the seed AND a record, so a verified seed costs no further
+// dependent load.  Half 0 is the record for reads that show the seed as stored; half 1 (used
+// only with canonical seeds) the record for reads that show its reverse complement - each is
+// written in the orientation of the reads that will be compared with it.  Words of a half:
+//   word 0   (half 0 only) bits 0..29 the seed, bit 30 = slot is free, bit 31 = some seed whose
+//            home is this slot lives further along (a miss must walk on); see ST_*
 //   word 1   info: bit j = some key designates this seed at offset j (its window starts j
 //            bases before the seed)
 //   word 2-4 nb, the NEIGHBOURHOOD: the 48 bases from E = k - s before the seed, 2 bits each,
@@ -135,7 +182,7 @@ __device__ __forceinline__ uint64_t ldg_u64_hint(const void *ptr, uint64_t pol) 
 // seed by chance (1 lookup in 1300 at s = 14 with 200 k seeds) costs a compare instead of
 // ~16 dependent key-table probes that miss L2.
 struct SeedTable {
-  uint4 *slots;      // 2 x uint4 per slot
+  uint4 *slots;      // 4 x uint4 per slot (2 per half)
   uint32_t n_slots;  // any size (not a power of two)
 };
 __host__ __device__ __forceinline__ uint32_t seed_next(uint32_t slot, uint32_t n_slots) {
@@ -194,6 +241,7 @@ struct ScanParams {
   KeyTable kt;
   uint32_t seed_mult;  // SEED_MULT << (32 - 2s): the product ignores bases beyond s
   uint32_t seed_mask;  // low 2s bits
+  uint32_t cshift;     // 32 - 2s (seed_revcomp)
   uint32_t four;       // = 4, opaque to the compiler: keeps the filter address on the FMA pipe
   uint32_t pw[32];     // pw[n] = 2^n, opaque too: multiplies by these stay on the FMA pipe
   uint32_t filter_words;  // = BLOOM_WORDS (shared-memory mode), as a run-time operand of the wide multiply

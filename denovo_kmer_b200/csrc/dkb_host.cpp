@@ -4,6 +4,7 @@
 // spanning k-mer entries for kernel 1).  The reference files are unmounted;
 // the semantics are DESIGN.md §2.  No CUDA in this file.
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -145,6 +146,7 @@ int dkb_pack_reads(const uint8_t *seq, const uint8_t *qual, const uint64_t *offs
   // output words are split between threads on 128-position boundaries: no sharing
   unsigned n_thr = std::thread::hardware_concurrency();
   if (n_thr > 32) n_thr = 32;
+  if (const char *e = getenv("DKB_PACK_THREADS")) n_thr = atoi(e) > 0 ? (unsigned)atoi(e) : n_thr;
   if (n_thr < 1 || n_pos < (1u << 20)) n_thr = 1;
   const uint64_t per = ((n_pos + n_thr - 1) / n_thr + 127) / 128 * 128;
   auto work = [&](unsigned t) {

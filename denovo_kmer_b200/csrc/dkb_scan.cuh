@@ -25,8 +25,12 @@
 
 namespace dkb {
 
-template <int D, int NH, bool GF, bool PROF>
+// FM = filter mode: 0 seed filter in shared memory, 1 in L2, 2 in L2 behind a one-bit
+// shared-memory pre-filter.
+template <int D, int NH, int FM, bool PROF>
 struct ScanWarp {
+  static constexpr bool GF = FM > 0, PRE = FM == 2;
+  static constexpr bool CANON = canon_for_mode(FM);  // seeds keyed by min(s-mer, its reverse complement)
   // Strides 8 and 16 leave 8 / 4 lookups per lane in a 2048-position tile; SUB such tiles
   // form a macro tile with 32 lookups per lane so that hit handling and loop overhead are
   // paid once per macro tile.
@@ -45,13 +49,15 @@ struct ScanWarp {
   uint32_t lt_mask;
   uint64_t keep = l2_policy_evict_last();  // cache policy of every table load
   const uint32_t zero;                     // 0, but not to the compiler
+  const uint32_t fbase;                    // shared-memory address of the (pre-)filter
   // stage B probes in flight (issued at the end of one tile, consumed in the next)
-  uint32_t pend_n = 0, pend_x = 0, pend_p = 0, pend_b = 0, pend_v = 0;
+  uint32_t pend_n = 0, pend_x = 0, pend_p = 0, pend_b = 0, pend_v = 0, pend_f = 0;
   unsigned long long n_bloom = 0, n_seed = 0, n_probe = 0, n_hit = 0;
 
   __device__ __forceinline__ ScanWarp(const ScanParams &p, const uint32_t *f, uint16_t *h,
                                       uint64_t *c, int l)
-      : P(p), filt(f), hl(h), cq(c), lane(l), lt_mask((1u << l) - 1), zero(p.four >> 3) {}
+      : P(p), filt(f), hl(h), cq(c), lane(l), lt_mask((1u << l) - 1), zero(p.four >> 3),
+        fbase((uint32_t)__cvta_generic_to_shared(f)) {}
 
   __device__ __forceinline__ uint32_t ld_bases(uint32_t wi) const {
     return wi < P.seg[cur].n_bwords ? __ldg(P.seg[cur].bases + wi) : 0u;
@@ -110,8 +116,9 @@ struct ScanWarp {
       p = (uint32_t)e;
       const uint32_t start = p > (uint32_t)E ? p - (uint32_t)E : 0u;
       const uint32_t bw0 = start >> 4, mw0 = start >> 5;
-      // the seed's slot = its record: the sector stage B already touched
-      const uint4 *rp = P.st.slots + 2 * (size_t)(uint32_t)(e >> 32);
+      // the record for this read orientation: a 32-byte half of the seed's slot (half 0 is
+      // the sector stage B already touched)
+      const uint4 *rp = P.st.slots + 2 * (size_t)(uint32_t)(e >> 32);  // e >> 32 = 2 * slot + flip
       const uint4 r0 = ldg_v4_hint(rp, keep), r1 = ldg_v4_hint(rp + 1, keep);
       const uint32_t nb0 = r0.z, nb1 = r0.w, nb2 = r1.x, wd0 = r1.y, wd1 = r1.z, wd2 = r1.w;
       uint32_t b[5], m[3];
@@ -221,9 +228,16 @@ struct ScanWarp {
     asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]));
   }
 
+  // s-mer (masked) -> the seed it is stored under, and whether that is its reverse complement
+  __device__ __forceinline__ uint32_t canon(uint32_t x, uint32_t &flip) const {
+    if constexpr (CANON) return seed_canon(x, P.cshift, flip);
+    flip = 0;
+    return x;
+  }
+
   // word 0 of a seed-table slot (the seed and its flags)
   __device__ __forceinline__ uint32_t ld_slot_word(uint32_t slot) const {
-    return ldg_u32_hint(reinterpret_cast<const uint32_t *>(P.st.slots) + 8 * (size_t)slot, keep);
+    return ldg_u32_hint(reinterpret_cast<const uint32_t *>(P.st.slots) + 16 * (size_t)slot, keep);
   }
 
   // Slow half of a seed-table lookup: the home slot holds another seed and carries
@@ -241,7 +255,7 @@ struct ScanWarp {
     }
   }
 
-  // Queue the lanes' verified seeds (seed-table slot, stream position) for stage C.
+  // Queue the lanes' verified seeds (2 * seed-table slot + read orientation, stream position) for stage C.
   __device__ __forceinline__ void push_verified(bool found, uint32_t slot, uint32_t p) {
 #if DKB_X == 6
     found = found && p == 0xFFFFFFFFu;  // timing experiment: no stage C
@@ -301,7 +315,7 @@ struct ScanWarp {
       if (r == 1) { v = lv[1]; x = lx[1]; }
       if (r == 2) { v = lv[2]; x = lx[2]; }
       if (r == 3) { v = lv[3]; x = lx[3]; }
-      const uint32_t i = 31u - ((lidx >> (8 * r)) & 31u);
+      const uint32_t i = 31u - ((lidx >> (8 * r)) & 31u), flip = (lidx >> (8 * r + 7)) & 1u;
       bool found = has && ((v ^ x) & ST_SEED_BITS) == 0;
       const bool moved = has && !found;  // flagged without a match: ST_MOVED_BIT
       uint32_t slot = seed_home(x, P.st.n_slots);
@@ -309,7 +323,7 @@ struct ScanWarp {
         if (moved) found = walk(x, slot);
         __syncwarp();
       }
-      push_verified(found, slot, lbase + lane * CHUNK + i * D);
+      push_verified(found, 2 * slot + flip, lbase + lane * CHUNK + i * D);
     } while (__any_sync(FULL_MASK, mm != 0));
   }
 
@@ -330,12 +344,13 @@ struct ScanWarp {
         const bool has = a != 0;
         const uint32_t b = 31u - __clz(a);  // any hit will do: take the highest bit
         a &= ~(1u << (b & 31));
-        const uint32_t x = cut_seed(w, b);
+        uint32_t flip;
+        const uint32_t x = canon(cut_seed(w, b), flip);
         lx[r] = x;
 #if DKB_X != 1
         if (has) lv[r] = ld_slot_word(seed_home(x, P.st.n_slots));
 #endif
-        lidx |= (b & 31) << (8 * r);
+        lidx |= ((b & 31) | flip << 7) << (8 * r);
       }
       if (!__any_sync(FULL_MASK, a != 0)) break;
       // a lane with more than NR hits in one tile (rare): finish these rounds now
@@ -361,7 +376,7 @@ struct ScanWarp {
       __syncwarp();
     }
     pend_n = 0;
-    push_verified(found, slot, pend_p);
+    push_verified(found, 2 * slot + pend_f, pend_p);
   }
 
   // ---- stage B, batch form, first half: start the exact check of hits [first, first + n)
@@ -380,7 +395,7 @@ struct ScanWarp {
       const uint32_t idx = id & 63;
       pend_p = tile_base + (idx / LPT) * WTILE + src * CHUNK + (idx % LPT) * D;
       const uint32_t wi = pend_p >> 4;
-      pend_x = __funnelshift_r(ld_bases(wi), ld_bases(wi + 1), 2 * (pend_p & 15)) & P.seed_mask;
+      pend_x = canon(__funnelshift_r(ld_bases(wi), ld_bases(wi + 1), 2 * (pend_p & 15)) & P.seed_mask, pend_f);
       pend_b = seed_home(pend_x, P.st.n_slots);
       if (act) pend_v = ld_slot_word(pend_b);
       pend_n = n;
@@ -395,7 +410,7 @@ struct ScanWarp {
     if (c == 1) { lo = v[1]; hi = v[2]; }
     if (c == 2) { lo = v[2]; hi = v[3]; }
     if (c == 3) { lo = v[3]; hi = v[4]; }
-    pend_x = __funnelshift_r(lo, hi, 2 * (q & 15)) & P.seed_mask;
+    pend_x = canon(__funnelshift_r(lo, hi, 2 * (q & 15)) & P.seed_mask, pend_f);
     pend_p = tile_base + src * CHUNK + q;
     pend_b = seed_home(pend_x, P.st.n_slots);
     if (act) pend_v = ld_slot_word(pend_b);
@@ -503,38 +518,18 @@ struct ScanWarp {
   // each and overlap; IMAD.WIDE 2.4; a multiply-high 5 and it holds up the ALU pipe, so
   // there is none here.  ALU: cut (caller), index shift, one shift per filter bit, AND.
   // FMA: hash, wide multiply, address, and the caller's accumulate.
-  __device__ __forceinline__ uint32_t lookup(uint32_t x, uint32_t mult, uint32_t fbase) const {
+  __device__ __forceinline__ uint32_t lookup(uint32_t x, uint32_t mult) const {
+    if constexpr (CANON) {
+      uint32_t flip;
+      x = seed_canon(x & P.seed_mask, P.cshift, flip);
+    }
     const uint32_t h = x * mult;
     unsigned long long prod;  // forced wide: ptxas would turn a plain (u64)h * n >> 32 into IMAD.HI
     uint32_t word;
-    if constexpr (GF) {
-      // large candidate sets: the filter does not fit in shared memory; probe it in L2 -
-      // behind a one-bit shared-memory pre-filter when the build chose one (an SM sustains
-      // one random L2 load per clock at best, so every lookup the pre-filter answers counts)
-      uint32_t hh = h;
-      bool pass = true;
-      if (P.pre_words) {
-        unsigned long long p1;
-        asm("mul.wide.u32 %0, %1, %2;" : "=l"(p1) : "r"(h), "r"(P.pre_words));
-        const uint32_t addr = (uint32_t)(p1 >> 32) * P.four + fbase;
-        uint32_t w1;
-        asm("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(addr));
-        pass = __funnelshift_r(w1, 0, (uint32_t)p1 >> 27) & 1u;
-        hh = h * PRE_REHASH;
-      }
-      asm("mul.wide.u32 %0, %1, %2;" : "=l"(prod) : "r"(hh), "r"(P.bloom_words));
-      word = 0;
-      // (no L1 allocation: the filter is far larger than L1, and leaving L1 to the loads
-      // that need it is worth 4 %; the same hint on stream or table loads costs 1-2 %)
-      if (pass)
-        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;"
-                     : "=r"(word) : "l"(P.bloom + (uint32_t)(prod >> 32)), "l"(keep));
-    } else {
-      asm("mul.wide.u32 %0, %1, %2;" : "=l"(prod) : "r"(h), "r"(P.filter_words));
-      // byte address = idx * 4 + base as a multiply-add (P.four is opaque), not an ALU-pipe LEA
-      const uint32_t addr = (uint32_t)(prod >> 32) * P.four + fbase;
-      asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(addr));
-    }
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(prod) : "r"(h), "r"(P.filter_words));
+    // byte address = idx * 4 + base as a multiply-add (P.four is opaque), not an ALU-pipe LEA
+    const uint32_t addr = (uint32_t)(prod >> 32) * P.four + fbase;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(addr));
     const uint32_t lo = (uint32_t)prod;
     uint32_t bit = __funnelshift_r(word, 0, x);  // the shift wraps: bit (x & 31) comes down to bit 0
     if (NH >= 2) bit &= __funnelshift_r(word, 0, lo >> 27);
@@ -543,20 +538,89 @@ struct ScanWarp {
     return bit & 1u;
   }
 
+  // ---- L2 filter mode: N lookups at once, in three passes so that the N shared-memory loads
+  // of the pre-filter, and then the N L2 loads behind it, are all in flight together (one
+  // lookup at a time, each load's latency was exposed in full: the LDS 30 cycles, the L2 load
+  // 300+, per lookup and warp).  x[i] = the s-mer of lookup first + i; returns a with the hit
+  // bits added at bit positions top - (first + i).
+  template <int N>
+  __device__ __forceinline__ uint32_t gf_lookups(const uint32_t (&xr)[N], uint32_t a, int top) const {
+    const uint32_t mult = P.seed_mult;
+    uint32_t x[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      x[i] = xr[i];
+      if constexpr (CANON) {
+        uint32_t flip;
+        x[i] = seed_canon(xr[i] & P.seed_mask, P.cshift, flip);
+      }
+    }
+    uint32_t h[N], w1[N];
+    if constexpr (PRE) {
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        h[i] = x[i] * mult;
+        unsigned long long p1;
+        asm("mul.wide.u32 %0, %1, %2;" : "=l"(p1) : "r"(h[i]), "r"(P.pre_words));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1[i]) : "r"((uint32_t)(p1 >> 32) * P.four + fbase));
+      }
+    }
+    uint32_t word[N], lo[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      const uint32_t hh = PRE ? h[i] * PRE_REHASH : x[i] * mult;
+      unsigned long long prod;
+      asm("mul.wide.u32 %0, %1, %2;" : "=l"(prod) : "r"(hh), "r"(P.bloom_words));
+      lo[i] = (uint32_t)prod;
+      word[i] = 0;
+      bool pass = true;
+      // pre-filter: bit (s-mer & 31) of the word (the funnel shift wraps its shift amount)
+      if constexpr (PRE) pass = (__funnelshift_r(w1[i], 0, x[i]) & 1u) != 0;
+      // address = base + 4 * word index as ONE wide multiply-add
+      unsigned long long ga;
+      asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(ga) : "r"((uint32_t)(prod >> 32)), "l"(P.bloom));
+      // (no L1 allocation: the filter is far larger than L1, and leaving L1 to the loads
+      // that need it is worth 4 %; the same hint on stream or table loads costs 1-2 %)
+      if (pass)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;"
+                     : "=r"(word[i]) : "l"(ga), "l"(keep));
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      uint32_t bit = __funnelshift_r(word[i], 0, x[i]);  // the shift wraps: bit (x & 31) comes down to bit 0
+      if (NH >= 2) bit &= __funnelshift_r(word[i], 0, lo[i] >> 27);
+      a = mad_pw(bit & 1u, top - i, a);
+    }
+    return a;
+  }
+
   // ---- stage A, macro-tile form: LPT lookups of one sub-tile, hit bits in the low bits,
   // first lookup highest.  At stride 16 every seed lies inside one word (s <= 15): no
   // cut, no halo.
   __device__ __forceinline__ uint32_t stage_a_sub(const uint32_t (&w)[5]) const {
     const uint32_t mult = P.seed_mult;
-    const uint32_t fbase = (uint32_t)__cvta_generic_to_shared(filt);
     uint32_t a = 0;
+    if constexpr (GF) {
+      constexpr int PERW = 16 / D;  // lookups per word (1 or 2)
+#pragma unroll
+      for (int c0 = 0; c0 < 4; c0 += 4 / PERW) {  // four lookups at a time
+        uint32_t x[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int c = c0 + i / PERW, t = (i % PERW) * D;
+          x[i] = t ? __funnelshift_r(w[c], w[c + 1], 2 * t) : w[c];
+        }
+        a = gf_lookups<4>(x, a, LPT - 1 - c0 * PERW);
+      }
+      return a;
+    }
     int n = 0;
 #pragma unroll
     for (int c = 0; c < 4; c++) {
 #pragma unroll
       for (int t = 0; t < 16; t += D, n++) {
         const uint32_t x = t ? __funnelshift_r(w[c], w[c + 1], 2 * t) : w[c];
-        a = mad_pw(lookup(x, mult, fbase), LPT - 1 - n, a);
+        a = mad_pw(lookup(x, mult), LPT - 1 - n, a);
       }
     }
     return a;
@@ -568,7 +632,6 @@ struct ScanWarp {
   __device__ __forceinline__ void stage_a(const uint32_t (&w)[5], uint32_t &acc0,
                                           uint32_t &acc1) const {
     const uint32_t mult = P.seed_mult;
-    const uint32_t fbase = (uint32_t)__cvta_generic_to_shared(filt);
     // Lookup n of the tile puts its hit bit at bit 31 - n of the mask (D == 1: of acc0 for
     // n < 32, of acc1 after) with a multiply-add by 2^(31 - n) from the parameter block -
     // the FMA pipe has the room, and a literal power of two would become an ALU-pipe shift.
@@ -578,11 +641,24 @@ struct ScanWarp {
 #pragma unroll
     for (int c = 0; c < 4; c++) {
       uint32_t a = 0;
+      if constexpr (GF) {  // strides 2 and 4: the word's 8 / 4 lookups, four at a time
 #pragma unroll
-      for (int t = 0; t < 16; t += D) {
-        const uint32_t x = t ? __funnelshift_r(w[c], w[c + 1], 2 * t) : w[c];
-        const int n = (c * NB + t / D) & 31;
-        a = mad_pw(lookup(x, mult, fbase), 31 - n, a);
+        for (int t0 = 0; t0 < 16; t0 += 4 * D) {
+          uint32_t x[4];
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int t = t0 + i * D;
+            x[i] = t ? __funnelshift_r(w[c], w[c + 1], 2 * t) : w[c];
+          }
+          a = gf_lookups<4>(x, a, 31 - ((c * NB + t0 / D) & 31));
+        }
+      } else {
+#pragma unroll
+        for (int t = 0; t < 16; t += D) {
+          const uint32_t x = t ? __funnelshift_r(w[c], w[c + 1], 2 * t) : w[c];
+          const int n = (c * NB + t / D) & 31;
+          a = mad_pw(lookup(x, mult), 31 - n, a);
+        }
       }
       part[c] = a;
     }
@@ -596,19 +672,48 @@ struct ScanWarp {
   }
 };
 
-// ---- stream loads -------------------------------------------------------------------
-// DKB_STREAM_LD selects how the macro path (strides 8, 16) reads the stream: 0 = plain
-// read-only loads at normal L2 priority (filter hits re-read their bases from L2 soon after),
-// 1 = evict-first (the stream is read once and must not push the filter and tables out of L2).
-#ifndef DKB_STREAM_LD
-#define DKB_STREAM_LD 1
-#endif
+// ---- stream loads (DKB_STREAM_LD: dkb_device.cuh) -------------------------------------
 __device__ __forceinline__ uint4 ld_stream_v4(const uint32_t *p) {
-#if DKB_STREAM_LD == 1
-  return __ldcs(reinterpret_cast<const uint4 *>(p));
-#else
+#if DKB_STREAM_LD == 0
   return __ldg(reinterpret_cast<const uint4 *>(p));
+#else
+  return __ldcs(reinterpret_cast<const uint4 *>(p));
 #endif
+}
+
+// TMA pieces: mbarrier + 1-D bulk copy global -> shared (shared addresses as 32-bit values)
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar,
+                                         uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
 }
 
 // tile -> registers.  Streaming (evict-first) loads: the stream is read once
@@ -651,8 +756,9 @@ struct UnitCursor {
   }
 };
 
-template <int D, int NH, bool GF, bool PROF>
+template <int D, int NH, int FM, bool PROF>
 __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
+  constexpr bool GF = FM > 0;
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t *filt = smem;
   uint64_t *cq_all = reinterpret_cast<uint64_t *>(smem + (GF ? P.pre_words : BLOOM_WORDS));
@@ -666,53 +772,36 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
   }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  ScanWarp<D, NH, GF, PROF> W(P, filt, hl_all + warp * HL_CAP, cq_all + warp * CQ_CAP, lane);
+  ScanWarp<D, NH, FM, PROF> W(P, filt, hl_all + warp * HL_CAP, cq_all + warp * CQ_CAP, lane);
 
   const uint32_t n_warps = gridDim.x * SCAN_WARPS;
   UnitCursor c{warp * gridDim.x + blockIdx.x, 0};  // consecutive units on different SMs
   c.settle_seg(P);
   W.cur = c.live(P) ? c.seg : 0;
-  if constexpr (ScanWarp<D, NH, GF, PROF>::MACRO) {
+  if constexpr (ScanWarp<D, NH, FM, PROF>::MACRO) {
     // Strides 8 / 16: a macro tile = SUB sub-tiles of 2048 positions (32 lookups per lane),
     // read in groups of GS sub-tiles (GS LDG.128 per lane in flight, 1-2 KB per warp), with
     // the next group prefetched while the current one is filtered.
-    constexpr int SUB = ScanWarp<D, NH, GF, PROF>::SUB, LPT = ScanWarp<D, NH, GF, PROF>::LPT;
-    constexpr int GS = 2, GPM = SUB / GS;  // sub-tiles per group, groups per macro tile
+    constexpr int SUB = ScanWarp<D, NH, FM, PROF>::SUB, LPT = ScanWarp<D, NH, FM, PROF>::LPT;
+    constexpr int GS = MACRO_GS, GPM = SUB / GS;  // sub-tiles per group, groups per macro tile
     constexpr bool HALO = D < 16;          // at stride 16 every seed lies inside one word
-    auto load_group = [&](const ScanSegment &S, uint32_t t0, uint4 (&v)[GS], uint32_t &edge) {
+    // a group that ends beyond the stream (the last one of a segment) is read word by word
+    auto load_group_tail = [&](const ScanSegment &S, uint32_t t0, uint4 (&v)[GS], uint32_t &edge) {
       const uint32_t wb = t0 * WTILE_WORDS + lane * 4;
-      if ((t0 + GS) * WTILE_WORDS + 4 <= S.n_bwords) {
 #pragma unroll
-        for (int j = 0; j < GS; j++) v[j] = ld_stream_v4(S.bases + wb + j * WTILE_WORDS);
-        edge = 0;
-        if (HALO && lane == 31) edge = __ldg(S.bases + (t0 + GS) * WTILE_WORDS);
-      } else {  // the stream ends inside this group
-#pragma unroll
-        for (int j = 0; j < GS; j++) {
-          const uint32_t q = wb + j * WTILE_WORDS;
-          v[j].x = q < S.n_bwords ? S.bases[q] : 0u;
-          v[j].y = q + 1 < S.n_bwords ? S.bases[q + 1] : 0u;
-          v[j].z = q + 2 < S.n_bwords ? S.bases[q + 2] : 0u;
-          v[j].w = q + 3 < S.n_bwords ? S.bases[q + 3] : 0u;
-        }
-        const uint32_t e = (t0 + GS) * WTILE_WORDS;
-        edge = HALO && e < S.n_bwords ? S.bases[e] : 0u;
+      for (int j = 0; j < GS; j++) {
+        const uint32_t q = wb + j * WTILE_WORDS;
+        v[j].x = q < S.n_bwords ? S.bases[q] : 0u;
+        v[j].y = q + 1 < S.n_bwords ? S.bases[q + 1] : 0u;
+        v[j].z = q + 2 < S.n_bwords ? S.bases[q + 2] : 0u;
+        v[j].w = q + 3 < S.n_bwords ? S.bases[q + 3] : 0u;
       }
+      const uint32_t e = (t0 + GS) * WTILE_WORDS;
+      edge = HALO && e < S.n_bwords ? S.bases[e] : 0u;
     };
-    int g = 0;
-    uint4 nxt[GS];
-    uint32_t nxt_edge = 0;
-    if (c.live(P)) load_group(P.seg[c.seg], c.local(P) * SUB, nxt, nxt_edge);
+    // stage A of one group +, after the last group of a macro tile, its hit handling
     uint32_t acc = 0;
-    while (c.live(P)) {
-      uint4 v[GS];
-#pragma unroll
-      for (int j = 0; j < GS; j++) v[j] = nxt[j];
-      const uint32_t edge = nxt_edge;
-      const uint32_t cur_macro = c.local(P);
-      const bool last_group = g == GPM - 1;
-      if (last_group) { c.unit += n_warps; c.settle_seg(P); g = 0; } else { g++; }
-      if (c.live(P)) load_group(P.seg[c.seg], c.local(P) * SUB + g * GS, nxt, nxt_edge);
+    auto filter_group = [&](const uint4 (&v)[GS], uint32_t edge) {
 #pragma unroll
       for (int j = 0; j < GS; j++) {
         uint32_t w[5] = {v[j].x, v[j].y, v[j].z, v[j].w, 0};
@@ -726,6 +815,110 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
         }
         acc = acc << LPT | W.stage_a_sub(w);
       }
+    };
+#if DKB_STREAM_LD == 2
+    // ---- TMA staging: per warp a ring of TMA_NST stages, one group (GS sub-tiles + the halo
+    // word's 16 bytes) each, filled by 1-D bulk copies that lane 0 issues and an mbarrier per
+    // stage completes.  The copy of the group TMA_NST ahead is issued when a stage has been
+    // consumed, so nothing of the stream is held in registers across a group and no stream
+    // load occupies an L1 line or a scoreboard of this warp.
+    uint8_t *ring_base = reinterpret_cast<uint8_t *>(hl_all + SCAN_WARPS * HL_CAP);
+    const uint32_t ring_a = (uint32_t)__cvta_generic_to_shared(ring_base) + warp * TMA_NST * TMA_STAGE_BYTES;
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(ring_base) +
+                           SCAN_WARPS * TMA_NST * TMA_STAGE_BYTES + warp * TMA_NST * 8;
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < TMA_NST; i++) mbar_init(bar_a + 8 * i, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const uint64_t stream_pol = l2_policy_evict_first();
+    struct GroupCursor {
+      UnitCursor u;
+      int g;
+    };
+    auto advance = [&](GroupCursor &q) {
+      if (++q.g == GPM) { q.u.unit += n_warps; q.u.settle_seg(P); q.g = 0; }
+    };
+    GroupCursor pc{c, 0}, cc{c, 0};
+    uint32_t direct = 0, phase = 0;  // one bit per stage: read word by word / mbarrier parity
+    auto issue = [&](int st) {       // the group at pc -> stage st
+      const ScanSegment &S = P.seg[pc.u.seg];
+      const uint32_t t0 = pc.u.local(P) * SUB + pc.g * GS;
+      if ((t0 + GS) * WTILE_WORDS + 4 <= S.n_bwords) {
+        direct &= ~(1u << st);
+        if (lane == 0) {
+          constexpr uint32_t bytes = HALO ? TMA_STAGE_BYTES : GS * 512;
+          mbar_expect_tx(bar_a + 8 * st, bytes);
+          bulk_g2s(ring_a + st * TMA_STAGE_BYTES, S.bases + (size_t)t0 * WTILE_WORDS, bytes, bar_a + 8 * st,
+                   stream_pol);
+        }
+      } else {
+        direct |= 1u << st;
+      }
+    };
+#pragma unroll
+    for (int i = 0; i < TMA_NST; i++)
+      if (pc.u.live(P)) { issue(i); advance(pc); }
+    int st = 0;
+    while (cc.u.live(P)) {
+      uint4 v[GS];
+      uint32_t edge = 0;
+      if ((direct >> st) & 1) {
+        load_group_tail(P.seg[cc.u.seg], cc.u.local(P) * SUB + cc.g * GS, v, edge);
+      } else {
+        mbar_wait(bar_a + 8 * st, (phase >> st) & 1);
+        phase ^= 1u << st;
+        const uint32_t sa = ring_a + st * TMA_STAGE_BYTES;
+#pragma unroll
+        for (int j = 0; j < GS; j++) v[j] = lds_v4(sa + j * 512 + lane * 16);
+        if (HALO) edge = lds_u32(sa + GS * 512);
+      }
+      const uint32_t cur_macro = cc.u.local(P);
+      const bool last_group = cc.g == GPM - 1;
+      advance(cc);
+      filter_group(v, edge);
+      // the stage's words have been used (stage A depends on them), so it can be refilled
+      __syncwarp();
+      if (pc.u.live(P)) { issue(st); advance(pc); }
+      st = st + 1 == TMA_NST ? 0 : st + 1;
+      if (last_group) {
+        W.consume_pending(acc);
+        const uint32_t w0[5] = {0, 0, 0, 0, 0};
+        W.handle_hits(acc, 0, w0, cur_macro * SUB * WTILE);
+        acc = 0;
+        if (cc.u.live(P) && cc.u.seg != W.cur) {  // the warp's next unit lies in another stream
+          W.drain();
+          W.cur = cc.u.seg;
+        }
+      }
+    }
+#else
+    auto load_group = [&](const ScanSegment &S, uint32_t t0, uint4 (&v)[GS], uint32_t &edge) {
+      const uint32_t wb = t0 * WTILE_WORDS + lane * 4;
+      if ((t0 + GS) * WTILE_WORDS + 4 <= S.n_bwords) {
+#pragma unroll
+        for (int j = 0; j < GS; j++) v[j] = ld_stream_v4(S.bases + wb + j * WTILE_WORDS);
+        edge = 0;
+        if (HALO && lane == 31) edge = __ldg(S.bases + (t0 + GS) * WTILE_WORDS);
+      } else {  // the stream ends inside this group
+        load_group_tail(S, t0, v, edge);
+      }
+    };
+    int g = 0;
+    uint4 nxt[GS];
+    uint32_t nxt_edge = 0;
+    if (c.live(P)) load_group(P.seg[c.seg], c.local(P) * SUB, nxt, nxt_edge);
+    while (c.live(P)) {
+      uint4 v[GS];
+#pragma unroll
+      for (int j = 0; j < GS; j++) v[j] = nxt[j];
+      const uint32_t edge = nxt_edge;
+      const uint32_t cur_macro = c.local(P);
+      const bool last_group = g == GPM - 1;
+      if (last_group) { c.unit += n_warps; c.settle_seg(P); g = 0; } else { g++; }
+      if (c.live(P)) load_group(P.seg[c.seg], c.local(P) * SUB + g * GS, nxt, nxt_edge);
+      filter_group(v, edge);
       if (last_group) {
         W.consume_pending(acc);
         // same scoreboard trap as in the tile path: settle the prefetched group first
@@ -742,10 +935,11 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
         }
       }
     }
+#endif
   } else {
   uint32_t nxt[5];
   if (c.live(P)) load_tile(P.seg[c.seg], c.local(P), lane, nxt);
-  if constexpr (ScanWarp<D, NH, GF, PROF>::LOCAL) {
+  if constexpr (ScanWarp<D, NH, FM, PROF>::LOCAL) {
     // Rotated loop: the table loads of tile t (its rounds) are issued at the top of
     // iteration t + 1, right after the prefetched words of tile t + 1 have been settled and
     // before tile t + 2 is requested; they are looked at after stage A of tile t + 1.  The

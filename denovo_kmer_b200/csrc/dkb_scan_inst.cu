@@ -1,6 +1,7 @@
 // dkb_scan_inst.cu - the instantiations of kernel 2 for ONE probe stride (DKB_INST_D = 1, 2,
 // 4, 8 or 16), compiled as its own translation unit so that the strides build in parallel.
-// Shared-memory filter: 1..4 filter bits; L2 filter (strides 2..16): 1..2 bits; each with and
+// Shared-memory filter: 1..4 filter bits; L2 filter with and without the pre-filter (strides
+// 2..16): 1..2 bits; each with and
 // without the profiling counters.  DKB_AB_BUILD (scripts/ab_build.sh): 2 filter bits only.
 #include "dkb_scan.cuh"
 
@@ -13,19 +14,20 @@
 namespace dkb {
 typedef void (*scan_fn)(const ScanParams);
 
-scan_fn DKB_CAT(pick_scan_d, DKB_INST_D)(int NH, bool gf, bool prof) {
+// fm: 0 = filter in shared memory, 1 = in L2, 2 = in L2 behind the shared-memory pre-filter
+scan_fn DKB_CAT(pick_scan_d, DKB_INST_D)(int NH, int fm, bool prof) {
   constexpr int D = DKB_INST_D;
-#define PICK(h, g)                                                                      \
-  if (NH == h && gf == g)                                                               \
-    return prof ? (scan_fn)k_scan<D, h, g, true> : (scan_fn)k_scan<D, h, g, false>;
-  PICK(2, false)
+#define PICK(h, m)                                                                      \
+  if (NH == h && fm == m)                                                               \
+    return prof ? (scan_fn)k_scan<D, h, m, true> : (scan_fn)k_scan<D, h, m, false>;
+  PICK(2, 0)
 #if DKB_INST_D >= 2
-  PICK(2, true)
+  PICK(2, 1) PICK(2, 2)
 #endif
 #ifndef DKB_AB_BUILD
-  PICK(1, false) PICK(3, false) PICK(4, false)
+  PICK(1, 0) PICK(3, 0) PICK(4, 0)
 #if DKB_INST_D >= 2
-  PICK(1, true)
+  PICK(1, 1) PICK(1, 2)
 #endif
 #endif
 #undef PICK

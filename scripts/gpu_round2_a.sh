@@ -9,12 +9,24 @@ mkdir -p gpurun_out
 python __graft_entry__.py smoke 2>&1 | tail -3
 timeout 2400 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_a.json 2> gpurun_out/bench_a.err; echo "ours rc=$?"; cat gpurun_out/bench_a.json; tail -5 gpurun_out/bench_a.err
-for v in ld0; do
+for v in base ld0; do
   DKB_LIBRARY=ab/libdkb_$v.so timeout 300 python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu-baseline > gpurun_out/bench_$v.json 2> gpurun_out/bench_$v.err; echo "$v rc=$?"
   python -c "
 import json,sys
 d=json.load(open('gpurun_out/bench_$v.json')); print('$v', d['value']/1e12, d['roofline']['frac'], d['wgs_shard']['value']/1e12, d['wgs_shard']['roofline']['frac'])"
 done
+for v in tma2 tma3; do
+  for pw in 26624 35584; do
+  DKB_PREFILTER_WORDS=$pw DKB_LIBRARY=ab/libdkb_$v.so timeout 300 python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu-baseline --no-wgs > gpurun_out/bench_${v}_$pw.json 2> gpurun_out/bench_${v}_$pw.err; echo "$v $pw rc=$?"
+  python -c "
+import json,sys
+d=json.load(open('gpurun_out/bench_${v}_$pw.json')); print('$v $pw', d['value']/1e12, d['roofline']['frac'])"
+  done
+done
+DKB_PREFILTER_WORDS=26624 timeout 300 python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu-baseline --no-wgs > gpurun_out/bench_ld1_26624.json 2> gpurun_out/bench_ld1_26624.err
+python -c "
+import json,sys
+d=json.load(open('gpurun_out/bench_ld1_26624.json')); print('ld1 26624', d['value']/1e12, d['roofline']['frac'])"
 for mb in 16 48; do
   DKB_L2_PERSIST_MB=$mb timeout 300 python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu-baseline > gpurun_out/bench_p$mb.json 2> gpurun_out/bench_p$mb.err; echo "persist $mb rc=$?"
   python -c "

@@ -51,8 +51,14 @@ def _run(dkb, orc, a, lowq_frac=None):
     torch.cuda.synchronize()
     with dkb.KmerCounter(a.k) as kc:
         kc.build_table(entries)
-        kc.submit_device_multi([(b2.data_ptr(), m1.data_ptr(), n_pos, s)
-                                for s, (b2, m1, n_pos, _) in enumerate(streams)])
+        per = ((1 << 32) - 4096) // 151 // 128 * 128 * 151   # one launch takes < 2^32 positions
+        if all(n_pos <= per for (_, _, n_pos, _) in streams):
+            kc.submit_device_multi([(b2.data_ptr(), m1.data_ptr(), n_pos, s)
+                                    for s, (b2, m1, n_pos, _) in enumerate(streams)])
+        else:  # 100x: 6.4 G positions per sample, cut after a multiple of 128 reads
+            for s, (b2, m1, n_pos, _) in enumerate(streams):
+                for p0 in range(0, n_pos, per):
+                    kc.submit_device(b2.data_ptr() + p0 // 4, m1.data_ptr() + p0 // 8, min(per, n_pos - p0), s)
         got = kc.entry_counts().copy()
         hits, dist, nk, calls = kc.finalise(THR)
         tun, st = kc.tuning(), kc.stats()
