@@ -48,6 +48,8 @@ struct dkb_ctx {
   uint32_t table_slots = 0;
   // seeds
   uint4 *d_sslots = nullptr;  // seed table: 64-byte slots (seed + two records), 4 x uint4 each
+  uint32_t *d_probe = nullptr;  // shared-memory filter mode: probe array in front of the slots
+  uint32_t probe_slots = 0;
   bool canon = false;         // seeds keyed by their strand-canonical form
   uint32_t seed_slots = 0;
   uint32_t n_seeds = 0;
@@ -132,8 +134,10 @@ void dfree(T *&p) {
 void free_table(dkb_ctx *c) {
   dfree(c->d_keys); dfree(c->d_variant); dfree(c->d_allele); dfree(c->d_dead);
   dfree(c->d_tslots);
-  dfree(c->d_sslots); dfree(c->d_bloom); dfree(c->d_pre);
-  dfree(c->d_counts); dfree(c->d_hits); dfree(c->d_distinct); dfree(c->d_nkmers);
+  dfree(c->d_sslots); dfree(c->d_probe); dfree(c->d_bloom); dfree(c->d_pre);
+  c->probe_slots = 0;
+  dfree(c->d_counts); dfree(c->d_hits);  // (d_distinct, d_nkmers live in d_hits' block)
+  c->d_distinct = c->d_nkmers = nullptr;
   dfree(c->d_calls);
   c->n_entries = c->n_live = 0;
   c->n_variants = 0;
@@ -296,6 +300,8 @@ SeedTable seed_table(const dkb_ctx *ctx) {
   SeedTable T;
   T.slots = ctx->d_sslots;
   T.n_slots = ctx->seed_slots;
+  T.probe = ctx->d_probe;
+  T.n_probe = ctx->probe_slots;
   return T;
 }
 
@@ -737,9 +743,9 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
     CU(cudaMalloc(&d_slot_of, n1 * 4));
     CU(cudaMalloc(&ctx->d_tslots, (size_t)ctx->table_slots * 16));
     CU(cudaMalloc(&ctx->d_counts, n1 * 3 * 4));
-    CU(cudaMalloc(&ctx->d_hits, nv1 * 6 * 4));
-    CU(cudaMalloc(&ctx->d_distinct, nv1 * 6 * 4));
-    CU(cudaMalloc(&ctx->d_nkmers, nv1 * 2 * 4));
+    CU(cudaMalloc(&ctx->d_hits, nv1 * 14 * 4));  // hits, distinct, n_kmers: one block, one memset per finalise
+    ctx->d_distinct = ctx->d_hits + nv1 * 6;
+    ctx->d_nkmers = ctx->d_hits + nv1 * 12;
     CU(cudaMalloc(&ctx->d_calls, nv1));
     CU(cudaMalloc(&d_nseeds, 4));
     CU(cudaMemsetAsync(ctx->d_tslots, 0xFF, (size_t)ctx->table_slots * 16, st));
@@ -794,6 +800,13 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
     if (want_slots >= 4294967295.0) return fail(ctx, DKB_EINVAL, "too many seeds for the seed table");
     ctx->seed_slots = (uint32_t)want_slots;
     CU(cudaMalloc(&ctx->d_sslots, (size_t)ctx->seed_slots * 64));
+    if (!ctx->gf && !getenv("DKB_NO_PROBE_ARRAY")) {  // probe array: 8 words per seed (dkb_device.cuh)
+      const double want_probe = 8.0 * n_seeds + 64;
+      if (want_probe >= 4294967295.0) return fail(ctx, DKB_EINVAL, "too many seeds for the probe array");
+      ctx->probe_slots = (uint32_t)want_probe;
+      CU(cudaMalloc(&ctx->d_probe, (size_t)ctx->probe_slots * 4));
+      CU(cudaMemsetAsync(ctx->d_probe, 0x40, (size_t)ctx->probe_slots * 4, st));  // ST_EMPTY
+    }
     CU(cudaMalloc(&d_cov, (size_t)ctx->seed_slots * 24));
     CU(cudaMemsetAsync(d_cov, 0, (size_t)ctx->seed_slots * 24, st));
     ctx->bloom_words = ctx->gf ? l2_filter_words((double)n_seeds) / 4 * 4 : (uint32_t)BLOOM_WORDS;
@@ -1001,7 +1014,7 @@ int dkb_counts_reset(dkb_ctx *ctx) {
   if (!ctx->d_counts) return fail(ctx, DKB_ESTATE, "dkb_table_build must come first");
   CU(cudaSetDevice(ctx->device));
   CU(cudaMemsetAsync(ctx->d_counts, 0, (ctx->n_entries ? ctx->n_entries : 1) * 3 * 4, ctx->s_scan));
-  CU(cudaMemsetAsync(ctx->d_prof, 0, 4 * sizeof(unsigned long long), ctx->s_scan));
+  if (ctx->prof) CU(cudaMemsetAsync(ctx->d_prof, 0, 4 * sizeof(unsigned long long), ctx->s_scan));
   ctx->finalised = false;
   return DKB_OK;
 }
@@ -1043,9 +1056,7 @@ namespace {
 int finalise_counts(dkb_ctx *ctx, const dkb_thresholds *thr, const uint32_t *d_counts) {
   cudaStream_t st = ctx->s_scan;
   const size_t nv1 = ctx->n_variants ? ctx->n_variants : 1;
-  CU(cudaMemsetAsync(ctx->d_hits, 0, nv1 * 6 * 4, st));
-  CU(cudaMemsetAsync(ctx->d_distinct, 0, nv1 * 6 * 4, st));
-  CU(cudaMemsetAsync(ctx->d_nkmers, 0, nv1 * 2 * 4, st));
+  CU(cudaMemsetAsync(ctx->d_hits, 0, nv1 * 14 * 4, st));
   const int TB = 256;
   if (ctx->n_entries)
     k_variant_reduce<<<(uint32_t)((ctx->n_entries + TB - 1) / TB), TB, 0, st>>>(
@@ -1216,6 +1227,10 @@ int dkb_stats_get(dkb_ctx *ctx, dkb_stats *out) {
 
 int dkb_profile_counters(dkb_ctx *ctx, int enable) {
   if (!ctx) return fail(nullptr, DKB_EINVAL, "ctx is null");
+  if (enable && !ctx->prof) {  // counters start from zero when profiling is switched on
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemsetAsync(ctx->d_prof, 0, 4 * sizeof(unsigned long long), ctx->s_scan));
+  }
   ctx->prof = enable != 0;
   return DKB_OK;
 }

@@ -100,6 +100,23 @@ __device__ __forceinline__ void seedtab_insert(const SeedTable &T, uint32_t seed
   }
 }
 
+// Same insertion into the probe array (one word per entry).
+__device__ __forceinline__ void probe_insert(const SeedTable &T, uint32_t seed) {
+  uint32_t e = seed_home(seed, T.n_probe);
+  bool home = true;
+  while (true) {
+    uint32_t old = *reinterpret_cast<volatile uint32_t *>(T.probe + e);
+    if (old & ST_FREE_BIT) {
+      old = atomicCAS(T.probe + e, ST_EMPTY, seed);
+      if (old == ST_EMPTY) old = seed;
+    }
+    if ((old & ST_SEED_BITS) == seed) return;
+    if (home) atomicOr(T.probe + e, ST_MOVED_BIT);
+    home = false;
+    e = seed_next(e, T.n_probe);
+  }
+}
+
 // Slot of a seed that is in the table.
 __device__ __forceinline__ uint32_t seedtab_find(const SeedTable &T, uint32_t seed) {
   uint32_t slot = seed_home(seed, T.n_slots);
@@ -251,6 +268,7 @@ __global__ void k_assign_seeds(const BuildParams B, int pass, uint32_t *set, uin
     } else if (pass == ASSIGN_INSERT) {
       offs |= (uint32_t)(j / D) << (W * (ori * D + c));
       seedtab_insert(T, seed);
+      if (T.n_probe) probe_insert(T, seed);
       uint32_t h = seed * seed_mult;
       if (pre_words) {  // one-bit pre-filter; the main filter behind it uses an independent hash
         atomicOr(pre + bloom_word(h, pre_words), 1u << (seed & 31));

@@ -29,7 +29,8 @@ constexpr size_t SCAN_SMEM_BYTES = (size_t)BLOOM_WORDS * 4 + SCAN_LISTS_BYTES;
 constexpr size_t SCAN_SMEM_BYTES_GF = SCAN_LISTS_BYTES;
 
 // DKB_STREAM_LD: how the macro path (strides 8, 16) reads the base stream.
-//   0  read-only loads at normal L2 priority        1  evict-first loads (default)
+//   0  read-only loads at normal L2 priority        3  evict-first loads
+//   1  (default) normal priority in the shared-memory filter mode, evict-first in the L2 modes
 //   2  TMA: one lane per warp issues a 1-D bulk copy (cp.async.bulk) of each group of
 //      sub-tiles into a per-warp shared-memory ring, completion on an mbarrier; the stream
 //      never touches the LSU/L1 path the filter lookups need
@@ -181,9 +182,17 @@ __device__ __forceinline__ uint64_t ldg_u64_hint(const void *ptr, uint64_t pol) 
 // table only for windows inside the matching run around the seed: an s-mer that equals a
 // seed by chance (1 lookup in 1300 at s = 14 with 200 k seeds) costs a compare instead of
 // ~16 dependent key-table probes that miss L2.
+// Shared-memory filter mode only: filter false positives are frequent there, and at the
+// slot table's load factor (1/2) a third of them would land on a slot that says "walk on".
+// A PROBE ARRAY in front takes them: one 4-byte word per entry (same ST_* encoding), 1/8 full,
+// so that an absent seed costs one 4-byte load (about one in a hundred a second one); only
+// seeds found in it go on to their slot.  n_probe = 0: no probe array (L2 filter modes,
+// where false positives are rare and true seeds would only pay an extra hop).
 struct SeedTable {
   uint4 *slots;      // 4 x uint4 per slot (2 per half)
   uint32_t n_slots;  // any size (not a power of two)
+  uint32_t *probe;
+  uint32_t n_probe;
 };
 __host__ __device__ __forceinline__ uint32_t seed_next(uint32_t slot, uint32_t n_slots) {
   return slot + 1 == n_slots ? 0u : slot + 1;

@@ -235,17 +235,34 @@ struct ScanWarp {
     return x;
   }
 
-  // word 0 of a seed-table slot (the seed and its flags)
-  __device__ __forceinline__ uint32_t ld_slot_word(uint32_t slot) const {
-    return ldg_u32_hint(reinterpret_cast<const uint32_t *>(P.st.slots) + 16 * (size_t)slot, keep);
+  // Stage B checks a seed against the probe array in the shared-memory filter mode and
+  // against the slot table itself in the L2 modes (dkb_device.cuh, SeedTable).
+  static constexpr bool PROBE = FM == 0;
+  __device__ __forceinline__ bool use_probe() const { return PROBE && P.st.n_probe != 0; }
+  __device__ __forceinline__ uint32_t vhome(uint32_t x) const {
+    return seed_home(x, use_probe() ? P.st.n_probe : P.st.n_slots);
+  }
+  // the word that says whether entry `e` holds a seed (and whether to walk on)
+  __device__ __forceinline__ uint32_t ld_slot_word(uint32_t e) const {
+    if (use_probe()) return ldg_u32_hint(P.st.probe + e, keep);
+    return ldg_u32_hint(reinterpret_cast<const uint32_t *>(P.st.slots) + 16 * (size_t)e, keep);
+  }
+  // entry of the structure stage B verified against -> the seed's slot
+  __device__ __forceinline__ uint32_t slot_of(uint32_t x, uint32_t e) const {
+    if (!use_probe()) return e;
+    uint32_t b = seed_home(x, P.st.n_slots);
+    while ((ldg_u32_hint(reinterpret_cast<const uint32_t *>(P.st.slots) + 16 * (size_t)b, keep) & ST_SEED_BITS) != x)
+      b = seed_next(b, P.st.n_slots);
+    return b;
   }
 
   // Slow half of a seed-table lookup: the home slot holds another seed and carries
   // ST_MOVED_BIT, so the seed may sit further along (linear probing, ends at a free slot).
   __device__ __forceinline__ bool walk(uint32_t x, uint32_t &slot) const {
     uint32_t b = slot;
+    const uint32_t n = use_probe() ? P.st.n_probe : P.st.n_slots;
     while (true) {
-      b = seed_next(b, P.st.n_slots);
+      b = seed_next(b, n);
       const uint32_t v = ld_slot_word(b);
       if ((v & ST_SEED_BITS) == x) {
         slot = b;
@@ -318,11 +335,12 @@ struct ScanWarp {
       const uint32_t i = 31u - ((lidx >> (8 * r)) & 31u), flip = (lidx >> (8 * r + 7)) & 1u;
       bool found = has && ((v ^ x) & ST_SEED_BITS) == 0;
       const bool moved = has && !found;  // flagged without a match: ST_MOVED_BIT
-      uint32_t slot = seed_home(x, P.st.n_slots);
+      uint32_t slot = vhome(x);
       if (__any_sync(FULL_MASK, moved)) {
         if (moved) found = walk(x, slot);
         __syncwarp();
       }
+      if (found) slot = slot_of(x, slot);
       push_verified(found, 2 * slot + flip, lbase + lane * CHUNK + i * D);
     } while (__any_sync(FULL_MASK, mm != 0));
   }
@@ -348,7 +366,7 @@ struct ScanWarp {
         const uint32_t x = canon(cut_seed(w, b), flip);
         lx[r] = x;
 #if DKB_X != 1
-        if (has) lv[r] = ld_slot_word(seed_home(x, P.st.n_slots));
+        if (has) lv[r] = ld_slot_word(vhome(x));
 #endif
         lidx |= ((b & 31) | flip << 7) << (8 * r);
       }
@@ -376,6 +394,7 @@ struct ScanWarp {
       __syncwarp();
     }
     pend_n = 0;
+    if (found) slot = slot_of(x, slot);
     push_verified(found, 2 * slot + pend_f, pend_p);
   }
 
@@ -396,7 +415,7 @@ struct ScanWarp {
       pend_p = tile_base + (idx / LPT) * WTILE + src * CHUNK + (idx % LPT) * D;
       const uint32_t wi = pend_p >> 4;
       pend_x = canon(__funnelshift_r(ld_bases(wi), ld_bases(wi + 1), 2 * (pend_p & 15)) & P.seed_mask, pend_f);
-      pend_b = seed_home(pend_x, P.st.n_slots);
+      pend_b = vhome(pend_x);
       if (act) pend_v = ld_slot_word(pend_b);
       pend_n = n;
       return;
@@ -412,7 +431,7 @@ struct ScanWarp {
     if (c == 3) { lo = v[3]; hi = v[4]; }
     pend_x = canon(__funnelshift_r(lo, hi, 2 * (q & 15)) & P.seed_mask, pend_f);
     pend_p = tile_base + src * CHUNK + q;
-    pend_b = seed_home(pend_x, P.st.n_slots);
+    pend_b = vhome(pend_x);
     if (act) pend_v = ld_slot_word(pend_b);
     pend_n = n;
   }
@@ -673,10 +692,17 @@ struct ScanWarp {
 };
 
 // ---- stream loads (DKB_STREAM_LD: dkb_device.cuh) -------------------------------------
+// Shared-memory filter mode: normal L2 priority - its filter hits are frequent and re-read
+// their bases from L2 right after (evict-first costs 6 % at 250 candidates).  L2 filter modes:
+// evict-first - hits are rare there, and the stream must not push the filter and the tables out.
+template <int FM>
 __device__ __forceinline__ uint4 ld_stream_v4(const uint32_t *p) {
 #if DKB_STREAM_LD == 0
   return __ldg(reinterpret_cast<const uint4 *>(p));
+#elif DKB_STREAM_LD == 3
+  return __ldcs(reinterpret_cast<const uint4 *>(p));
 #else
+  if (FM == 0) return __ldg(reinterpret_cast<const uint4 *>(p));
   return __ldcs(reinterpret_cast<const uint4 *>(p));
 #endif
 }
@@ -898,7 +924,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
       const uint32_t wb = t0 * WTILE_WORDS + lane * 4;
       if ((t0 + GS) * WTILE_WORDS + 4 <= S.n_bwords) {
 #pragma unroll
-        for (int j = 0; j < GS; j++) v[j] = ld_stream_v4(S.bases + wb + j * WTILE_WORDS);
+        for (int j = 0; j < GS; j++) v[j] = ld_stream_v4<FM>(S.bases + wb + j * WTILE_WORDS);
         edge = 0;
         if (HALO && lane == 31) edge = __ldg(S.bases + (t0 + GS) * WTILE_WORDS);
       } else {  // the stream ends inside this group
