@@ -212,8 +212,9 @@ double tile_cost(double n_entries, bool hints, int k, int s, int D, int NH, bool
   const double chance_cost = 25.0 * table * lookups_tile * chance;
   double l2_lookup = 119.0;
   if (pre) l2_lookup = 22.0 + 105.0 * (1.0 - exp(-seeds / (32.0 * pre_filter_words(true))));
-  if (D >= 8)
-    return 61.0 + lookups_lane * (gf ? l2_lookup : 16.0 + NH) + 16.0 * table * hits + chance_cost;
+  if (D >= 8)  // (round-2 refit: the probe array and normal-priority stream loads made the shared-memory mode cheaper)
+    return (gf ? 61.0 : 37.0) + lookups_lane * (gf ? l2_lookup : 16.0 + NH) + (gf ? 16.0 : 14.6) * table * hits +
+           chance_cost;
   return 100.0 + lookups_lane * (gf ? l2_lookup : 13.0 + 1.5 * NH) + 9.0 * table * (hits < 64 ? hits : 64) +
          (hits > 64 ? 14.0 * table * (hits - 64) : 0.0) + chance_cost;
 }
@@ -790,11 +791,11 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
     CU(cudaMemcpyAsync(&n_seeds, d_nseeds, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     ctx->n_seeds = n_seeds;
-    // Seed table: 64-byte slots (seed + a 32-byte record per read orientation), half full, any
+    // Seed table: 64-byte slots (seed + a 32-byte record per read orientation), a quarter full, any
     // size.  Only occupied slots are ever touched by true hits, so the hot set is 32 B per seed
     // and orientation; an absent seed (a filter false positive) lands on a slot marked
     // ST_MOVED_BIT - a second load - about one time in 8.
-    double per_seed = 2.0;
+    double per_seed = 4.0;  // (2.0: 3 % slower on configs[1] - displaced seeds cost a dependent load per step)
     if (const char *e = getenv("DKB_SEED_SLOTS_PER_SEED")) per_seed = atof(e) >= 1.1 ? atof(e) : per_seed;
     const double want_slots = per_seed * n_seeds + 64;
     if (want_slots >= 4294967295.0) return fail(ctx, DKB_EINVAL, "too many seeds for the seed table");
