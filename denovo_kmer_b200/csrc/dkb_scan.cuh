@@ -19,7 +19,7 @@
 
 #ifndef DKB_X
 // Timing experiments only, wrong counts (scripts/ab_build.sh; DESIGN.md §4 "where the time goes"):
-// 1 rounds without their load, 2 no rounds, 6 no stage C.
+// 1 rounds without their load, 2 no rounds, 6 no stage C, 7 no hit handling at all (macro path).
 #define DKB_X 0
 #endif
 
@@ -47,7 +47,11 @@ struct ScanWarp {
   uint32_t ch = 0, ct = 0;
   int lane;
   uint32_t lt_mask;
-  uint64_t keep = l2_policy_evict_last();  // cache policy of every table load
+#ifndef DKB_TABLE_POLICY
+#define DKB_TABLE_POLICY 0  // experiment: 0 evict-last for every table load, 1 normal for slot/key/probe loads
+#endif
+  uint64_t keep = l2_policy_evict_last();  // cache policy of the filter loads ...
+  uint64_t keep_t = DKB_TABLE_POLICY == 0 ? l2_policy_evict_last() : l2_policy_normal();  // ... and of the table loads
   const uint32_t zero;                     // 0, but not to the compiler
   const uint32_t fbase;                    // shared-memory address of the (pre-)filter
   // stage B probes in flight (issued at the end of one tile, consumed in the next)
@@ -81,7 +85,7 @@ struct ScanWarp {
     uint32_t *const counts = P.seg[cur].counts;
     while (true) {
       const uint4 *bp = P.kt.slots + bk * KBUCKET;
-      const uint4 s0 = ldg_v4_hint(bp, keep), s1 = ldg_v4_hint(bp + 1, keep);
+      const uint4 s0 = ldg_v4_hint(bp, keep_t), s1 = ldg_v4_hint(bp + 1, keep_t);
       const uint64_t k0 = slot_key(s0), k1 = slot_key(s1);
       if (k0 == key && s0.z != ENTRY_DEAD && slot_offset(s0.w, ori, j % D, D) == (uint32_t)j) {
         atomicAdd(counts + s0.z, 1u);
@@ -119,7 +123,7 @@ struct ScanWarp {
       // the record for this read orientation: a 32-byte half of the seed's slot (half 0 is
       // the sector stage B already touched)
       const uint4 *rp = P.st.slots + 2 * (size_t)(uint32_t)(e >> 32);  // e >> 32 = 2 * slot + flip
-      const uint4 r0 = ldg_v4_hint(rp, keep), r1 = ldg_v4_hint(rp + 1, keep);
+      const uint4 r0 = ldg_v4_hint(rp, keep_t), r1 = ldg_v4_hint(rp + 1, keep_t);
       const uint32_t nb0 = r0.z, nb1 = r0.w, nb2 = r1.x, wd0 = r1.y, wd1 = r1.z, wd2 = r1.w;
       uint32_t b[5], m[3];
 #pragma unroll
@@ -244,14 +248,14 @@ struct ScanWarp {
   }
   // the word that says whether entry `e` holds a seed (and whether to walk on)
   __device__ __forceinline__ uint32_t ld_slot_word(uint32_t e) const {
-    if (use_probe()) return ldg_u32_hint(P.st.probe + e, keep);
-    return ldg_u32_hint(reinterpret_cast<const uint32_t *>(P.st.slots) + 16 * (size_t)e, keep);
+    if (use_probe()) return ldg_u32_hint(P.st.probe + e, keep_t);
+    return ldg_u32_hint(reinterpret_cast<const uint32_t *>(P.st.slots) + 16 * (size_t)e, keep_t);
   }
   // entry of the structure stage B verified against -> the seed's slot
   __device__ __forceinline__ uint32_t slot_of(uint32_t x, uint32_t e) const {
     if (!use_probe()) return e;
     uint32_t b = seed_home(x, P.st.n_slots);
-    while ((ldg_u32_hint(reinterpret_cast<const uint32_t *>(P.st.slots) + 16 * (size_t)b, keep) & ST_SEED_BITS) != x)
+    while ((ldg_u32_hint(reinterpret_cast<const uint32_t *>(P.st.slots) + 16 * (size_t)b, keep_t) & ST_SEED_BITS) != x)
       b = seed_next(b, P.st.n_slots);
     return b;
   }
@@ -600,9 +604,17 @@ struct ScanWarp {
       asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(ga) : "r"((uint32_t)(prod >> 32)), "l"(P.bloom));
       // (no L1 allocation: the filter is far larger than L1, and leaving L1 to the loads
       // that need it is worth 4 %; the same hint on stream or table loads costs 1-2 %)
-      if (pass)
+#ifndef DKB_FILTER_POLICY
+#define DKB_FILTER_POLICY 0  // experiment: 0 evict-last hint, 1 no hint
+#endif
+      if (pass) {
+#if DKB_FILTER_POLICY == 0
         asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;"
                      : "=r"(word[i]) : "l"(ga), "l"(keep));
+#else
+        asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(word[i]) : "l"(ga));
+#endif
+      }
     }
 #pragma unroll
     for (int i = 0; i < N; i++) {
@@ -953,7 +965,11 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
           asm volatile("" : "+r"(nxt[j].x), "+r"(nxt[j].y), "+r"(nxt[j].z), "+r"(nxt[j].w));
         asm volatile("" : "+r"(nxt_edge));
         const uint32_t w0[5] = {0, 0, 0, 0, 0};
+#if DKB_X != 7  // (7: timing / traffic experiment without any hit handling)
         W.handle_hits(acc, 0, w0, cur_macro * SUB * WTILE);
+#else
+        asm volatile("" ::"r"(acc));  // the lookups stay
+#endif
         acc = 0;
         if (c.live(P) && c.seg != W.cur) {  // the warp's next unit lies in another stream
           W.drain();

@@ -3,7 +3,7 @@ under profiles/: <R>_launches.csv (our kernels, per launch), <R>_scan_ncu.txt (r
 stalls, per-stage instruction split) and scan_traffic.json (DRAM bytes per scan launch,
 read by bench.py for roofline.traffic).  Usage: python scripts/make_profile_summary.py r1"""
 import collections, csv, io, json, os, re, subprocess, sys
-R = sys.argv[1] if len(sys.argv) > 1 else "r1"
+R = sys.argv[1] if len(sys.argv) > 1 else "r2"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
@@ -20,7 +20,7 @@ for r in rows:
     launches.append((int(d["ID"]), d["Kernel Name"].split("(")[0].replace("void ", ""), d["Grid Size"],
                      d["Block Size"], float(d["Metric Value"].replace(",", ""))))
 with open(os.path.join(out_dir, f"{R}_launches.csv"), "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ on: python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline\n")
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ on: python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-wgs\n")
     f.write("# per-launch times are cold-cache and serialised: compare shares, not absolutes\n")
     f.write("id,kernel,grid,block,duration_ns\n")
     for l in launches:
@@ -60,10 +60,15 @@ def to_bytes(d, key):
     v = num(d[key]); u = units[h.index(key)]
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
 
-lines = [f"ncu --set full --clock-control none --import-source on -k regex:k_scan -s 9 -c 3 on: python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline",
+want += ["l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+         "l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_hit.sum", "lts__t_sectors_srcunit_tex_op_read.sum",
+         "lts__t_sectors_srcunit_tex_op_read_lookup_hit.sum", "lts__t_sectors_srcunit_tex_op_read_lookup_miss.sum",
+         "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_global_ld.sum"]
+lines = [f"ncu --set full --clock-control none --import-source on -k regex:k_scan -s 3 -c 2 on: python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-wgs",
+         "(one launch scans the three samples of the trio: 1.4496 GB of 2-bit stream, 5.76 Gbases)",
          f"kernel: {recs[0].get('Kernel Name')} grid {recs[0].get('Grid Size')} block {recs[0].get('Block Size')}", ""]
 for i, d in enumerate(recs):
-    lines.append(f"launch {i} (sample {i % 3}):")
+    lines.append(f"launch {i}:")
     for w in want:
         if w in d:
             lines.append(f"  {w:72s} {d[w]} {units[h.index(w)]}")
@@ -72,9 +77,29 @@ for i, d in enumerate(recs):
         lines.append(f"  stall/issue {x.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', ''):28s} {v:.3f}")
     lines.append("")
 dram = [to_bytes(d, "dram__bytes_read.sum") + to_bytes(d, "dram__bytes_write.sum") for d in recs]
-json.dump({"dram_bytes_per_launch": sum(dram) / len(dram), "launches": len(dram), "round": R,
-           "source": f"profiles/{R}_scan_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, cold L2 per launch)"},
-          open(os.path.join(out_dir, "scan_traffic.json"), "w"))
+traffic = {"dram_bytes_per_launch": sum(dram) / len(dram), "launches": len(dram), "round": R,
+           "source": f"profiles/{R}_scan_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, cold L2 per launch; "
+                     "a launch = the three samples of a step)"}
+wrep = os.path.join(ROOT, "gpurun_out", f"prof_scan_wgs_{R}.ncu-rep")
+if os.path.exists(wrep):  # the WGS-shard capture: one launch
+    wraw = subprocess.run(["ncu", "-i", wrep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    wr = list(csv.reader(io.StringIO(wraw)))
+    wh, wu = wr[0], wr[1]
+    wlines = ["ncu --set full --clock-control none -k regex:k_scan -s 3 -c 1 on: python bench.py --steps 2 --warmup 3 --no-e2e "
+              "--no-cpu-baseline --genome-mb 128 --variants 4000 --table-variants 100000",
+              "(one shard of BASELINE.json configs[2]: 2.8992 GB of 2-bit stream per launch, 11.52 Gbases, 100 000-candidate table)", ""]
+    for d in [dict(zip(wh, r)) for r in wr[2:]]:
+        for w in want:
+            if w in d:
+                wlines.append(f"  {w:72s} {d[w]} {wu[wh.index(w)]}")
+        st = [(x, num(d[x])) for x in wh if "issue_stalled" in x and x.endswith("per_issue_active.ratio") and num(d[x]) is not None]
+        for x, v in sorted(st, key=lambda t: -t[1])[:7]:
+            wlines.append(f"  stall/issue {x.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', ''):28s} {v:.3f}")
+        def wb(key):
+            return num(d[key]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(wu[wh.index(key)], 1)
+        traffic["wgs_dram_bytes_per_launch"] = wb("dram__bytes_read.sum") + wb("dram__bytes_write.sum")
+    open(os.path.join(out_dir, f"{R}_scan_wgs_ncu.txt"), "w").write("\n".join(wlines) + "\n")
+json.dump(traffic, open(os.path.join(out_dir, "scan_traffic.json"), "w"))
 
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
                      capture_output=True, text=True).stdout
