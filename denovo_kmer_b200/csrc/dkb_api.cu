@@ -146,9 +146,12 @@ void free_table(dkb_ctx *c) {
 }
 
 // Words of the L2-resident seed filter: 64 bits per seed, between the shared-memory size
-// and 16 MB (it shares L2 with the tables and the stream; DKB_L2_FILTER_MAX_WORDS overrides).
+// and 32 MB (it shares L2 with the tables and the stream; DKB_L2_FILTER_MAX_WORDS overrides).
+// Measured on the 100 000-candidate WGS shard (6 M seeds): 4 / 8 / 16 / 32 / 48 MB -> 2.89 / 3.65 /
+// 3.86 / 3.92 / 3.91 Tbases/s: below 16 MB the filter's false positives (each a DRAM access
+// into the 1.5 GB slot table) cost more than the filter's own L2 misses.
 uint32_t l2_filter_words(double seeds) {
-  double cap = 4.0 * 1024 * 1024;  // 16 MB: larger filters start missing L2 (measured, profiles/README.md)
+  double cap = 8.0 * 1024 * 1024;  // 32 MB
   if (const char *e = getenv("DKB_L2_FILTER_MAX_WORDS")) cap = atof(e);
   double w = seeds * 2.0;
   if (w > cap) w = cap;

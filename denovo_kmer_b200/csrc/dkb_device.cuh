@@ -111,9 +111,11 @@ __host__ __device__ constexpr bool canon_for_mode(int fm) { return DKB_CANON == 
 // Reverse complement of an s-mer held in the low 2s bits (stream order either way: first base
 // least significant), cshift = 32 - 2s; x must be masked to its 2s bits.
 __device__ __forceinline__ uint32_t seed_revcomp(uint32_t x, uint32_t cshift) {
-  uint32_t r = __brev(x);  // bases reversed (now in the top 2s bits), the two bits of each base swapped
-  r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);  // swap them back
-  return ~r >> cshift;     // complement and realign (the ones below the s-mer are shifted out)
+  const uint32_t r = __brev(x);  // bases reversed (now in the top 2s bits), the two bits of each base swapped
+  // swap them back and complement in ONE LOP3: ~(((r >> 1) & 0x55555555) | ((r << 1) & ~0x55555555))
+  uint32_t c;
+  asm("lop3.b32 %0, %1, %2, 0x55555555, 0x1B;" : "=r"(c) : "r"(r >> 1), "r"(r << 1));
+  return c >> cshift;      // realign (the ones below the s-mer are shifted out)
 }
 // Canonical seed and whether the s-mer had to be flipped to get it.
 __device__ __forceinline__ uint32_t seed_canon(uint32_t x, uint32_t cshift, uint32_t &flip) {
