@@ -196,7 +196,7 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
@@ -220,19 +220,25 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         self.th.join(timeout=2)
-        sm, mx, reasons = [], None, set()
+        sm, busy, mx, reasons = [], [], None, set()
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
             except (ValueError, IndexError):
                 continue
+            try:  # "under load": the GPU was busy in that sample's window
+                if float(r[7]) >= 50:
+                    busy.append(sm[-1])
+            except (ValueError, IndexError):
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
                                 "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        use = busy or sm
+        return {"sm_mhz": float(np.median(use)) if use else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm), "samples_under_load": len(busy)}
 
 
 def measured_peak_gbs():
@@ -385,11 +391,11 @@ def run_ours(a):
     job = Job(a, rank, world, local, tdist)
     kc = job.kc
     sampler = ClockSampler(local)
-    if rank == 0:  # clocks are sampled from the warm-up steps to the end of the timed region
-        sampler.start()
+    if rank == 0:  # clocks are sampled from the warm-up steps on: the timed region (tens of ms)
+        sampler.start()  # and, in the same record, the e2e and wgs_shard legs that follow it
         time.sleep(0.1)
     ms_max, s0, s1 = job.timed(a.steps, max(a.warmup, 3))
-    clocks = sampler.stop() if rank == 0 else None
+    n_clock_timed = len(sampler.rows)
     total_bases = job.bases_per_step * world  # weak: N shards; strong: the split trio's parts
     value = total_bases * a.steps / (ms_max * 1e-3)
     hits, distinct, n_kmers, calls = kc.results()
@@ -574,7 +580,7 @@ def run_ours(a):
                        "e2e_equals_device_resident": e2e["counts_equal_device_resident_run"] if e2e else None},
             # per step: 1 scan launch (the trio) + k_variant_reduce + k_calls
             "gpu_launches": int((s1["scan_launches"] - s0["scan_launches"]) + 2 * a.steps),
-            "clocks": clocks,
+            "clocks": None,  # filled in when the sampler stops, after the last leg
         }
     job.close()
     del job
@@ -607,6 +613,8 @@ def run_ours(a):
         wj.close()
 
     if rank == 0:
+        out["clocks"] = sampler.stop()
+        out["clocks"]["samples_by_end_of_timed_region"] = n_clock_timed
         print(json.dumps(out))
     if world > 1:
         tdist.destroy_process_group()
