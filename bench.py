@@ -446,17 +446,61 @@ def run_ours(a):
             host.append((hb, hm, n_pos))
         job.streams = None
         torch.cuda.empty_cache()
-        reads_per_batch = 4_194_304  # multiple of 128 reads -> batches start on word boundaries
+        reads_per_batch = 4_194_304  # 2^22 reads: batches start on 2048-position block boundaries
         pos_per_batch = reads_per_batch * (READ_LEN + 1)
+        import denovo_kmer_b200 as dkb_pkg
+        # the same batches with their flags as zero lists (dkb_mask_to_zero_list): what the
+        # headline e2e sends; the dense-flag form is measured beside it
+        sparse = []
+        for s_, (hb, hm, n_pos) in enumerate(host):
+            for p0 in range(0, n_pos, pos_per_batch):
+                n = min(pos_per_batch, n_pos - p0)
+                zoff, zbytes = dkb_pkg.mask_to_zero_list(hm[p0 // 32: p0 // 32 + (n + 127) // 128 * 4], n)
+                pz = kc.host_alloc(len(zoff))
+                pz[:] = zoff
+                pb = kc.host_alloc((len(zbytes) + 3) // 4).view(np.uint8)[: len(zbytes)]
+                pb[:] = zbytes
+                sparse.append((s_, hb[p0 // 16:], pz, pb, n))
+        sparse_bytes = job.stream_bytes + sum(z.nbytes + b.nbytes for (_, _, z, b, _) in sparse)
 
-        def e2e_step():
+        def e2e_step(dense):
             kc.reset_counts()
-            for s, (hb, hm, n_pos) in enumerate(host):
-                for p0 in range(0, n_pos, pos_per_batch):
-                    n = min(pos_per_batch, n_pos - p0)
-                    kc._ck(kc._L.dkb_batch_submit(kc._h, hb.ctypes.data + p0 // 4, hm.ctypes.data + p0 // 8, n, s))
+            if dense:
+                for s, (hb, hm, n_pos) in enumerate(host):
+                    for p0 in range(0, n_pos, pos_per_batch):
+                        n = min(pos_per_batch, n_pos - p0)
+                        kc._ck(kc._L.dkb_batch_submit(kc._h, hb.ctypes.data + p0 // 4, hm.ctypes.data + p0 // 8, n, s))
+            else:
+                for (s, hb, pz, pb, n) in sparse:
+                    kc._ck(kc._L.dkb_batch_submit_sparse(kc._h, hb.ctypes.data, pz.ctypes.data, pb.ctypes.data,
+                                                         len(pb), n, s))
             kc.counts_allreduce()  # N>1: ncclAllReduce on the scan stream; no-op on one GPU
             return kc.finalise(THRESHOLDS)  # kernel 3 + D2H of hits/distinct/n_kmers/calls
+
+        def e2e_timed(dense):
+            e2e_step(dense)
+            job.barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(job.ext)
+            t0 = time.perf_counter()
+            for _ in range(a.e2e_steps):
+                res = e2e_step(dense)
+            ev1.record(job.ext)
+            own_s = time.perf_counter() - t0  # this rank's own steps (results fetched: all copies done)
+            job.barrier()
+            wall = time.perf_counter() - t0
+            t_e = torch.tensor([max(ev0.elapsed_time(ev1) * 1e-3, wall)], dtype=torch.float64, device=dev)
+            nbytes = (job.stream_bytes + job.mask_bytes) if dense else sparse_bytes
+            h2d_rate = torch.tensor([nbytes * a.e2e_steps / own_s / 1e9], dtype=torch.float64, device=dev)
+            rates = [h2d_rate.clone() for _ in range(world)]
+            if world > 1:
+                tdist.all_reduce(t_e, op=tdist.ReduceOp.MAX)
+                tdist.all_gather(rates, h2d_rate)
+            same = bool(np.array_equal(kc.entry_counts(), ref_counts))
+            return {"value": total_bases * a.e2e_steps / float(t_e.item()), "unit": UNIT,
+                    "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(sum(x.nbytes for x in res)),
+                    "steps": a.e2e_steps, "counts_equal_device_resident_run": same,
+                    "h2d_gbs_per_rank": [round(float(r.item()), 2) for r in rates]}
 
         # the box's H2D ceiling for this job: every rank copies its pinned batches to the device
         # at once, nothing else running (torch copy = cudaMemcpyAsync; not the product path)
@@ -475,32 +519,17 @@ def run_ours(a):
             tdist.all_gather(ceils, ceil_rate)
         del dst
 
-        e2e_step()
-        job.barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(job.ext)
-        t0 = time.perf_counter()
-        for _ in range(a.e2e_steps):
-            res = e2e_step()
-        ev1.record(job.ext)
-        own_s = time.perf_counter() - t0  # this rank's own steps (results fetched: all copies done)
-        job.barrier()
-        wall = time.perf_counter() - t0
-        t_e = torch.tensor([max(ev0.elapsed_time(ev1) * 1e-3, wall)], dtype=torch.float64, device=dev)
-        h2d_rate = torch.tensor([(job.stream_bytes + job.mask_bytes) * a.e2e_steps / own_s / 1e9],
-                                dtype=torch.float64, device=dev)
-        rates = [h2d_rate.clone() for _ in range(world)]
-        if world > 1:
-            tdist.all_reduce(t_e, op=tdist.ReduceOp.MAX)
-            tdist.all_gather(rates, h2d_rate)
-        same = bool(np.array_equal(kc.entry_counts(), ref_counts))
-        d2h = sum(x.nbytes for x in res)
-        e2e = {"value": total_bases * a.e2e_steps / float(t_e.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(job.stream_bytes + job.mask_bytes), "d2h_bytes_per_step": int(d2h),
-               "steps": a.e2e_steps, "counts_equal_device_resident_run": same,
-               "h2d_gbs_per_rank": [round(float(r.item()), 2) for r in rates],
-               "h2d_ceiling_gbs_per_rank": [round(float(r.item()), 2) for r in ceils],
-               "staging": f"dkb_host_alloc (cudaHostAlloc on the GPU's NUMA node; rank 0: node {job.numa_node})"}
+        dense_e2e = e2e_timed(True)
+        e2e = e2e_timed(False)
+        e2e["flags"] = "zero list (dkb_batch_submit_sparse): %.4f bytes per read base over PCIe" % (
+            sparse_bytes / job.bases_per_step)
+        e2e["dense_flags"] = {k_: dense_e2e[k_] for k_ in ("value", "h2d_bytes_per_step", "h2d_gbs_per_rank",
+                                                            "counts_equal_device_resident_run")}
+        e2e["counts_equal_device_resident_run"] = bool(e2e["counts_equal_device_resident_run"] and
+                                                        dense_e2e["counts_equal_device_resident_run"])
+        e2e["h2d_ceiling_gbs_per_rank"] = [round(float(r.item()), 2) for r in ceils]
+        e2e["staging"] = f"dkb_host_alloc (cudaHostAlloc on the GPU's NUMA node; rank 0: node {job.numa_node})"
+        del sparse
         del host
 
     # ---- the feeders (f1), rank 0 at N = 1: host packer rate, and an end-to-end leg through the

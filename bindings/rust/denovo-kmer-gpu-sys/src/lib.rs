@@ -52,6 +52,9 @@ extern "C" {
     pub fn dkb_pack_reads(seq: *const u8, qual: *const u8, offsets: *const u64, n_reads: usize,
                           min_baseq: c_int, bases2: *mut u32, mask1: *mut u32,
                           n_positions_out: *mut u64) -> c_int;
+    pub fn dkb_zero_list_blocks(n_positions: u64) -> usize;
+    pub fn dkb_mask_to_zero_list(mask1: *const u32, n_positions: u64, zoff: *mut u32, zbytes: *mut u8,
+                                 zbytes_cap: usize, zbytes_used: *mut usize) -> c_int;
     pub fn dkb_variant_kmers(left: *const *const c_char, r#ref: *const *const c_char,
                              alt: *const *const c_char, right: *const *const c_char,
                              n_variants: usize, k: c_int, drop_shared: c_int, keys: *mut u64,
@@ -62,6 +65,8 @@ extern "C" {
                            n_entries: usize, n_variants: u32) -> c_int;
     pub fn dkb_batch_submit(ctx: *mut DkbCtx, bases2: *const u32, mask1: *const u32,
                             n_positions: u64, sample: c_int) -> c_int;
+    pub fn dkb_batch_submit_sparse(ctx: *mut DkbCtx, bases2: *const u32, zoff: *const u32, zbytes: *const u8,
+                                   zbytes_used: usize, n_positions: u64, sample: c_int) -> c_int;
     pub fn dkb_batch_submit_reads(ctx: *mut DkbCtx, seq: *const u8, seq_format: c_int, qual: *const u8,
                                   offsets: *const u64, n_reads: usize, min_baseq: c_int, sample: c_int) -> c_int;
     pub fn dkb_batch_submit_device(ctx: *mut DkbCtx, d_bases2: *const u32, d_mask1: *const u32,

@@ -89,6 +89,20 @@ def pack_reads(seq, qual, offsets, min_baseq: int = DEFAULT_MIN_BASEQ, pinned: b
     return ReadStream(bases2, mask1, int(out.value), n_bases)
 
 
+def mask_to_zero_list(mask1, n_positions: int):
+    """Dense flags -> zero list (include/dkb.h): (zoff uint32[n_blocks + 1], zbytes uint8[used])."""
+    L = _lib.lib()
+    mask1 = np.ascontiguousarray(mask1).view(np.uint32)
+    nb = int(L.dkb_zero_list_blocks(n_positions))
+    zoff = np.zeros(nb + 1, dtype=np.uint32)
+    used = C.c_size_t(0)
+    check(L.dkb_mask_to_zero_list(_p(mask1, u32p), n_positions, _p(zoff, u32p), None, 0, C.byref(used)))
+    zbytes = np.zeros(max(int(used.value), 1), dtype=np.uint8)
+    check(L.dkb_mask_to_zero_list(_p(mask1, u32p), n_positions, _p(zoff, u32p), _p(zbytes, u8p),
+                                  len(zbytes), C.byref(used)))
+    return zoff, zbytes[: int(used.value)]
+
+
 # ---- spanning k-mer entries -----------------------------------------------------------
 @dataclass
 class KmerEntries:
@@ -195,6 +209,12 @@ class KmerCounter:
         self._keep.append(stream)
         self._ck(self._L.dkb_batch_submit(self._h, stream.bases2.ctypes.data,
                                           stream.mask1.ctypes.data, stream.n_positions, sample))
+
+    def submit_sparse(self, bases2, zoff, zbytes, n_positions: int, sample: int):
+        """Host buffers with the flags as a zero list (mask_to_zero_list): less PCIe traffic."""
+        self._keep.append((bases2, zoff, zbytes))
+        self._ck(self._L.dkb_batch_submit_sparse(self._h, bases2.ctypes.data, zoff.ctypes.data,
+                                                 zbytes.ctypes.data, len(zbytes), n_positions, sample))
 
     def submit_reads(self, seq, qual, offsets, sample: int, min_baseq: int = DEFAULT_MIN_BASEQ,
                      four_bit: bool = False):

@@ -79,6 +79,10 @@ struct dkb_ctx {
     uint8_t *seq = nullptr, *qual = nullptr;
     uint64_t *offsets = nullptr, *nib = nullptr;
     size_t seq_cap = 0, qual_cap = 0, off_cap = 0, nib_cap = 0;  // bytes / elements
+    // zero list of dkb_batch_submit_sparse
+    uint32_t *zoff = nullptr;
+    uint8_t *zbytes = nullptr;
+    size_t zoff_cap = 0, zbytes_cap = 0;
     cudaEvent_t copied = nullptr, freed = nullptr;
     bool in_use = false;
   } stage[2];
@@ -665,6 +669,8 @@ int dkb_ctx_destroy(dkb_ctx *ctx) {
     dfree(st.qual);
     dfree(st.offsets);
     dfree(st.nib);
+    dfree(st.zoff);
+    dfree(st.zbytes);
     if (st.copied) cudaEventDestroy(st.copied);
     if (st.freed) cudaEventDestroy(st.freed);
   }
@@ -927,6 +933,45 @@ int dkb_batch_submit(dkb_ctx *ctx, const uint32_t *bases2, const uint32_t *mask1
   CU(cudaEventRecord(st.copied, ctx->s_copy));
   CU(cudaStreamWaitEvent(ctx->s_scan, st.copied, 0));
   int rc = launch_scan(ctx, st.bases, st.mask, n_positions, sample);
+  if (rc != DKB_OK) return rc;
+  CU(cudaEventRecord(st.freed, ctx->s_scan));
+  st.in_use = true;
+  return DKB_OK;
+}
+
+int dkb_batch_submit_sparse(dkb_ctx *ctx, const uint32_t *bases2, const uint32_t *zoff,
+                            const uint8_t *zbytes, size_t zbytes_used, uint64_t n_positions, int sample) {
+  if (!ctx) return fail(nullptr, DKB_EINVAL, "ctx is null");
+  if (!ctx->d_tslots) return fail(ctx, DKB_ESTATE, "dkb_table_build must come first");
+  if (sample < 0 || sample >= DKB_N_SAMPLES) return fail(ctx, DKB_EINVAL, "sample must be 0, 1 or 2");
+  if (n_positions == 0) return DKB_OK;
+  if (n_positions > 0xFFFFF000ull) return fail(ctx, DKB_EINVAL, "batch too long (max 2^32 - 4096 positions)");
+  if (!bases2 || !zoff || (zbytes_used && !zbytes)) return fail(ctx, DKB_EINVAL, "null stream pointer");
+  const size_t nb = dkb_zero_list_blocks(n_positions);
+  if ((zoff[nb] & 0x7FFFFFFFu) != zbytes_used) return fail(ctx, DKB_EINVAL, "zoff[n_blocks] != zbytes_used");
+  CU(cudaSetDevice(ctx->device));
+  const size_t bw = dkb_stream_bases_words(n_positions), mw = dkb_stream_mask_words(n_positions);
+  dkb_ctx::Stage &st = ctx->stage[ctx->next_stage];
+  ctx->next_stage ^= 1;
+  const size_t zb1 = zbytes_used ? zbytes_used : 1;
+  if (st.in_use) CU(cudaStreamWaitEvent(ctx->s_copy, st.freed, 0));
+  int rc;
+  if (st.bases_cap < bw || st.mask_cap < mw || st.zoff_cap < nb + 1 || st.zbytes_cap < zb1) {
+    if (st.in_use) CU(cudaEventSynchronize(st.freed));  // the previous scan may still read the old buffers
+    if ((rc = grow(ctx, st.bases, st.bases_cap, bw)) != DKB_OK) return rc;
+    if ((rc = grow(ctx, st.mask, st.mask_cap, mw)) != DKB_OK) return rc;
+    if ((rc = grow(ctx, st.zoff, st.zoff_cap, nb + 1)) != DKB_OK) return rc;
+    if ((rc = grow(ctx, st.zbytes, st.zbytes_cap, zb1)) != DKB_OK) return rc;
+  }
+  CU(cudaMemcpyAsync(st.bases, bases2, bw * 4, cudaMemcpyHostToDevice, ctx->s_copy));
+  CU(cudaMemcpyAsync(st.zoff, zoff, (nb + 1) * 4, cudaMemcpyHostToDevice, ctx->s_copy));
+  if (zbytes_used) CU(cudaMemcpyAsync(st.zbytes, zbytes, zbytes_used, cudaMemcpyHostToDevice, ctx->s_copy));
+  CU(cudaEventRecord(st.copied, ctx->s_copy));
+  CU(cudaStreamWaitEvent(ctx->s_scan, st.copied, 0));
+  k_expand_zero_list<<<(uint32_t)((nb + 7) / 8), 256, 0, ctx->s_scan>>>(st.zoff, st.zbytes, (uint32_t)nb,
+                                                                      (uint32_t)mw, st.mask);
+  CU(cudaGetLastError());
+  rc = launch_scan(ctx, st.bases, st.mask, n_positions, sample);
   if (rc != DKB_OK) return rc;
   CU(cudaEventRecord(st.freed, ctx->s_scan));
   st.in_use = true;

@@ -169,6 +169,106 @@ int dkb_pack_reads(const uint8_t *seq, const uint8_t *qual, const uint64_t *offs
   return DKB_OK;
 }
 
+// ---- dense flags -> zero list (include/dkb.h) ---------------------------------------------
+namespace {
+constexpr uint64_t ZL_BLOCK = 2048;
+constexpr uint32_t ZL_RAW_BIT = 0x80000000u;
+
+inline bool flag_at(const uint32_t *mask1, uint64_t p) { return (mask1[p >> 5] >> (p & 31)) & 1u; }
+
+// Bytes the gap coding of block [p0, p1) needs (p0 a multiple of 32); positions >= n_pos of the
+// last block are not coded.  Word at a time: the zeros of a word are found with ctz.
+size_t zl_block_bytes(const uint32_t *mask1, uint64_t p0, uint64_t p1, uint8_t *out) {
+  size_t n = 0;
+  uint64_t gap = 0;
+  for (uint64_t wp = p0; wp < p1; wp += 32) {
+    const uint32_t valid = p1 - wp >= 32 ? 0xFFFFFFFFu : (1u << (p1 - wp)) - 1u;  // positions of this word in range
+    uint32_t zeros = ~mask1[wp >> 5] & valid;
+    uint32_t done = 0;  // positions of the word already accounted for
+    while (zeros) {
+      const uint32_t t = (uint32_t)__builtin_ctz(zeros);
+      zeros &= zeros - 1;
+      gap += t - done;
+      done = t + 1;
+      while (gap >= 255) {
+        if (out) out[n] = 255;
+        n++;
+        gap -= 255;
+      }
+      if (out) out[n] = (uint8_t)gap;
+      n++;
+      gap = 0;
+    }
+    gap += (uint32_t)__builtin_popcount(valid) - done;
+  }
+  return n;
+}
+}  // namespace
+
+size_t dkb_zero_list_blocks(uint64_t n_positions) { return (size_t)((n_positions + ZL_BLOCK - 1) / ZL_BLOCK); }
+
+int dkb_mask_to_zero_list(const uint32_t *mask1, uint64_t n_positions, uint32_t *zoff, uint8_t *zbytes,
+                          size_t zbytes_cap, size_t *zbytes_used) {
+  if (!zbytes_used || (n_positions && (!mask1 || !zoff))) return DKB_EINVAL;
+  const size_t nb = dkb_zero_list_blocks(n_positions);
+  if (nb >= 0x7FFFFFFFu / 256) return DKB_EINVAL;
+  // pass 1: size of every block (gap coding, or the plain 256 bytes when that is shorter)
+  std::vector<uint32_t> len(nb);
+  unsigned n_thr = std::thread::hardware_concurrency();
+  if (n_thr > 32) n_thr = 32;
+  if (const char *e = getenv("DKB_PACK_THREADS")) n_thr = atoi(e) > 0 ? (unsigned)atoi(e) : n_thr;
+  if (n_thr < 1 || nb < 64) n_thr = 1;
+  auto parallel = [&](auto &&fn) {
+    if (n_thr == 1) return fn(0, nb);
+    std::vector<std::thread> pool;
+    const size_t per = (nb + n_thr - 1) / n_thr;
+    for (unsigned t = 0; t < n_thr; t++) {
+      const size_t a = (size_t)t * per, b = a + per < nb ? a + per : nb;
+      if (a < b) pool.emplace_back(fn, a, b);
+    }
+    for (auto &th : pool) th.join();
+  };
+  auto span = [&](size_t b, uint64_t &p0, uint64_t &p1) {
+    p0 = (uint64_t)b * ZL_BLOCK;
+    p1 = p0 + ZL_BLOCK < n_positions ? p0 + ZL_BLOCK : n_positions;
+  };
+  parallel([&](size_t a, size_t b) {
+    for (size_t i = a; i < b; i++) {
+      uint64_t p0, p1;
+      span(i, p0, p1);
+      const size_t g = zl_block_bytes(mask1, p0, p1, nullptr);
+      len[i] = g > 256 ? (256u | ZL_RAW_BIT) : (uint32_t)g;
+    }
+  });
+  size_t total = 0;
+  for (size_t i = 0; i < nb; i++) {
+    zoff[i] = (uint32_t)total | (len[i] & ZL_RAW_BIT);
+    total += len[i] & ~ZL_RAW_BIT;
+  }
+  if (n_positions) zoff[nb] = (uint32_t)total;
+  *zbytes_used = total;
+  if (!zbytes) return DKB_OK;  // sizing call
+  if (total > zbytes_cap) return DKB_EINVAL;
+  parallel([&](size_t a, size_t b) {
+    for (size_t i = a; i < b; i++) {
+      uint64_t p0, p1;
+      span(i, p0, p1);
+      uint8_t *dst = zbytes + (zoff[i] & ~ZL_RAW_BIT);
+      if (zoff[i] & ZL_RAW_BIT) {  // the block's 64 mask words, little-endian; words past the stream are 0
+        for (uint32_t wi = 0; wi < 64; wi++) {
+          const uint64_t m = p0 / 32 + wi;
+          uint32_t v = m * 32 < n_positions ? mask1[m] : 0u;
+          if (m * 32 + 32 > n_positions && m * 32 < n_positions) v &= (1u << (n_positions - m * 32)) - 1u;
+          for (int k = 0; k < 4; k++) dst[4 * wi + k] = (uint8_t)(v >> (8 * k));
+        }
+      } else {
+        zl_block_bytes(mask1, p0, p1, dst);
+      }
+    }
+  });
+  return DKB_OK;
+}
+
 int dkb_variant_kmers(const char *const *left, const char *const *ref, const char *const *alt,
                       const char *const *right, size_t n_variants, int k, int drop_shared,
                       uint64_t *keys, uint32_t *variant_ids, uint8_t *allele_ids,

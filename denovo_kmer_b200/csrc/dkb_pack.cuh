@@ -75,4 +75,57 @@ __global__ void k_pack(const PackParams Q) {
   Q.mask1[m] = mk;
 }
 
+// ---- zero list -> dense flags --------------------------------------------------------
+// The flags of a stream can travel as a ZERO LIST instead of one bit per position (format:
+// include/dkb.h, dkb_mask_to_zero_list): per block of ZL_BLOCK positions a byte string "skip g
+// usable positions, then one unusable one" (255 = skip 255, no zero), or the block's plain bits
+// when that is shorter.  One warp expands one block into its 64 mask words.
+constexpr uint32_t ZL_BLOCK = 2048;           // positions per block = 64 mask words
+constexpr uint32_t ZL_RAW_BIT = 0x80000000u;  // in zoff[b]: the block is stored as plain bits (256 bytes)
+
+__global__ void k_expand_zero_list(const uint32_t *zoff, const uint8_t *zbytes, uint32_t n_blocks,
+                                   uint32_t n_mwords, uint32_t *mask1) {
+  __shared__ uint32_t sm[8][64];  // blockDim = 256: 8 warps
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t b = blockIdx.x * 8 + warp;
+  if (b >= n_blocks) return;
+  uint32_t *w = sm[warp];
+  const uint32_t o0 = zoff[b], o1 = zoff[b + 1] & ~ZL_RAW_BIT;
+  const uint8_t *src = zbytes + (o0 & ~ZL_RAW_BIT);
+  if (o0 & ZL_RAW_BIT) {  // plain bits, little-endian words
+    for (int i = lane; i < 64; i += 32) {
+      uint32_t v = 0;
+      for (int k = 0; k < 4; k++) v |= (uint32_t)src[4 * i + k] << (8 * k);
+      w[i] = v;
+    }
+  } else {
+    w[lane] = 0xFFFFFFFFu;
+    w[lane + 32] = 0xFFFFFFFFu;
+    __syncwarp();
+    const uint32_t n = o1 - (o0 & ~ZL_RAW_BIT);
+    uint32_t carry = 0;  // positions consumed so far
+    for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+      const uint32_t i = i0 + lane;
+      const uint32_t v = i < n ? src[i] : 255u;
+      const uint32_t adv = i < n ? (v == 255u ? 255u : v + 1u) : 0u;
+      uint32_t incl = adv;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL_MASK, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (i < n && v != 255u) {
+        const uint32_t pos = carry + incl - 1u;  // the zero position, inside the block
+        if (pos < ZL_BLOCK) atomicAnd(&w[pos >> 5], ~(1u << (pos & 31)));
+      }
+      carry += __shfl_sync(FULL_MASK, incl, 31);
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < 64; i += 32) {
+    const size_t m = (size_t)b * 64 + i;
+    if (m < n_mwords) mask1[m] = w[i];
+  }
+}
+
 }  // namespace dkb

@@ -168,6 +168,36 @@ def pack_stream(seq, qual, offsets, min_bq=0):
     return bases2, mask1, n_pos
 
 
+def expand_zero_list(zoff, zbytes, n_positions):
+    """Plain-Python reading of the zero-list form of the flags (include/dkb.h): returns the
+    flags of positions [0, n_positions) as a uint8 array.  Checks the host encoder and the
+    device expander."""
+    flags = np.ones(n_positions, dtype=np.uint8)
+    nb = (n_positions + 2047) // 2048
+    assert len(zoff) == nb + 1
+    for b in range(nb):
+        p0 = b * 2048
+        o0, o1 = int(zoff[b]), int(zoff[b + 1]) & 0x7FFFFFFF
+        raw = bool(o0 >> 31)
+        o0 &= 0x7FFFFFFF
+        if raw:
+            assert o1 - o0 == 256
+            bits = np.unpackbits(np.asarray(zbytes[o0:o1], dtype=np.uint8), bitorder="little")
+            n = min(2048, n_positions - p0)
+            flags[p0:p0 + n] = bits[:n]
+            continue
+        p = p0
+        for v in np.asarray(zbytes[o0:o1]).tolist():
+            if v == 255:
+                p += 255
+            else:
+                p += v
+                assert p < min(p0 + 2048, n_positions), "zero beyond its block"
+                flags[p] = 0
+                p += 1
+    return flags
+
+
 def calls(hits, distinct, thr):
     """thr = (min_child_alt_hits, min_child_alt_distinct, max_parent_alt_hits, min_parent_ref_hits)"""
     hits = np.ascontiguousarray(hits, dtype=np.uint64)

@@ -342,3 +342,35 @@ def test_padding_bits_beyond_the_stream_are_ignored(dkb, orc):
                 kc.submit_device(b.data_ptr(), m.data_ptr(), n_pos, 0)
                 assert np.array_equal(kc.entry_counts()[0].astype(np.uint64), want), (cut_reads, tuning)
     assert want.sum() > 0
+
+
+@pytest.mark.parametrize("tuning", [None, (15, 16, 2, 2), (14, 4, 2, 1)])
+def test_zero_list_submit_equals_dense_submit(dkb, orc, tuning):
+    """dkb_batch_submit_sparse (flags as a zero list, expanded on the device) gives the counters
+    of the dense form and of the oracle; batches that end inside a block, a read made of N only
+    (a plain-bits block) and an empty zero list included."""
+    k = 31
+    trio = synth.make_trio_host(120_000, 12, 25, k, seed=93, n_rate=0.004, lowq_frac=0.06)
+    ent = dkb.variant_kmers(trio.variant_tuples(), k)
+    ks = orc.KmerSet(ent.keys, ent.variant, ent.allele)
+    want = np.zeros((3, len(ent)), dtype=np.uint64)
+    with dkb.KmerCounter(k, tuning=tuning) as kc:
+        kc.build_table(ent)
+        for smp in range(3):
+            seq, qual, off = trio.reads[smp]
+            seq = seq.copy()
+            if smp == 1:
+                seq[int(off[10]):int(off[30])] = ord("N")   # twenty reads of N: dense zeros
+            if smp == 2:
+                qual = None                                  # hardly any zeros besides the separators
+                seq[seq == ord("N")] = ord("A")
+            ks.count_reads(seq, qual, off, k, 20, counts=want[smp])
+            cuts = [0, 7, (len(off) - 1) // 2, len(off) - 1]
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                lo, hi = int(off[a]), int(off[b])
+                st = dkb.pack_reads(seq[lo:hi], None if qual is None else qual[lo:hi], off[a:b + 1] - off[a], 20)
+                zoff, zbytes = dkb.mask_to_zero_list(st.mask1, st.n_positions)
+                kc.submit_sparse(st.bases2, zoff, zbytes, st.n_positions, smp)
+        got = kc.entry_counts()
+    assert np.array_equal(got.astype(np.uint64), want), tuning
+    assert want.sum() > 0

@@ -301,3 +301,39 @@ def test_rust_safe_crate_uses_only_declared_symbols():
     for m in re.findall(r"(?:kc|packer)\.(\w+)\(", example):
         assert m in methods, f"examples/trio.rs calls {m}() which the safe crate does not define"
     assert "impl Drop for Counter" in safe and "Result<" in safe
+
+
+def test_zero_list_round_trip(dkb, orc):
+    """dkb_mask_to_zero_list against the plain-Python reading of the format: random flags of
+    several densities, runs of >= 255 usable positions (escape bytes), dense-zero blocks (stored
+    as plain bits), lengths that end inside a block / a word, a packed real trio."""
+    import numpy as np
+    from denovo_kmer_b200 import synth
+    rng = np.random.default_rng(11)
+
+    def check(flags):
+        n = len(flags)
+        mw = (n + 127) // 128 * 4
+        bits = np.zeros(mw * 32, dtype=np.uint8)
+        bits[:n] = flags
+        bits[n:] = rng.integers(0, 2, size=len(bits) - n)  # padding must not matter
+        mask1 = np.packbits(bits, bitorder="little").view(np.uint32)
+        zoff, zbytes = dkb.mask_to_zero_list(mask1, n)
+        assert len(zoff) == (n + 2047) // 2048 + 1 and int(zoff[-1]) == len(zbytes)
+        back = orc.expand_zero_list(zoff, zbytes, n)
+        assert np.array_equal(back, flags), n
+        return len(zbytes)
+
+    for n in (1, 31, 2047, 2048, 2049, 5000, 70_001):
+        for dens in (0.0, 0.002, 0.04, 0.5, 1.0):
+            check((rng.random(n) >= dens).astype(np.uint8))
+    f = np.ones(10_000, dtype=np.uint8)
+    f[[0, 254, 255, 256, 600, 2047, 2048, 9_999]] = 0      # gaps of 253, 0, 0, 343 (escape), ...
+    check(f)
+    f = np.ones(6000, dtype=np.uint8)
+    f[2048:4096] = 0                                         # a whole block of zeros: plain bits
+    assert check(f) == 256
+    trio = synth.make_trio_host(30_000, 10, 5, 31, seed=9)
+    st = dkb.pack_reads(*trio.reads[0], 20)
+    used = check(np.unpackbits(st.mask1.view(np.uint8), bitorder="little")[: st.n_positions])
+    assert used < st.n_positions / 8 * 0.5  # less than half of the dense flags' bytes
