@@ -153,6 +153,12 @@ impl Counter {
     /// batch must not be repacked before [`Counter::sync`] (the packer's two-buffer rotation
     /// guarantees that when `sync` is called every second batch; see [`BatchPacker::next`]).
     pub fn submit(&mut self, b: &PinnedBatch, sample: i32) -> Result<()> {
+        if b.zbytes_used != usize::MAX {
+            // the packer made a zero list of the flags: a quarter less PCIe traffic
+            return self.ck(unsafe {
+                sys::dkb_batch_submit_sparse(self.ctx, b.bases2, b.zoff, b.zbytes, b.zbytes_used, b.n_positions, sample)
+            });
+        }
         self.ck(unsafe { sys::dkb_batch_submit(self.ctx, b.bases2, b.mask1, b.n_positions, sample) })
     }
 
@@ -247,6 +253,10 @@ pub fn comm_unique_id() -> Result<[u8; sys::DKB_COMM_ID_BYTES]> {
 pub struct PinnedBatch {
     bases2: *mut u32,
     mask1: *mut u32,
+    zoff: *mut u32,   // the flags as a zero list (dkb_mask_to_zero_list), also pinned
+    zbytes: *mut u8,
+    zbytes_cap: usize,
+    zbytes_used: usize, // usize::MAX: no zero list, submit the dense flags
     cap_bw: usize,
     cap_mw: usize,
     pub n_positions: u64,
@@ -265,12 +275,17 @@ impl BatchPacker {
     fn new(c: &mut Counter, max_reads: usize, max_bases: usize, min_baseq: i32) -> Result<Self> {
         let n_pos = (max_bases + max_reads) as u64;
         let (bw, mw) = unsafe { (sys::dkb_stream_bases_words(n_pos), sys::dkb_stream_mask_words(n_pos)) };
+        let nb = unsafe { sys::dkb_zero_list_blocks(n_pos) };
+        let zcap = mw * 4; // a zero list is never longer than the dense flags
         let mut mk = || -> Result<PinnedBatch> {
-            let (mut b, mut m) = (ptr::null_mut(), ptr::null_mut());
+            let (mut b, mut m, mut zo, mut zb) = (ptr::null_mut(), ptr::null_mut(), ptr::null_mut(), ptr::null_mut());
             check(unsafe { sys::dkb_host_alloc(c.ctx, bw * 4, &mut b) }, c.ctx)?;
             check(unsafe { sys::dkb_host_alloc(c.ctx, mw * 4, &mut m) }, c.ctx)?;
-            Ok(PinnedBatch { bases2: b as *mut u32, mask1: m as *mut u32, cap_bw: bw, cap_mw: mw,
-                             n_positions: 0, n_bases: 0 })
+            check(unsafe { sys::dkb_host_alloc(c.ctx, (nb + 1) * 4, &mut zo) }, c.ctx)?;
+            check(unsafe { sys::dkb_host_alloc(c.ctx, zcap, &mut zb) }, c.ctx)?;
+            Ok(PinnedBatch { bases2: b as *mut u32, mask1: m as *mut u32, zoff: zo as *mut u32,
+                             zbytes: zb as *mut u8, zbytes_cap: zcap, zbytes_used: usize::MAX,
+                             cap_bw: bw, cap_mw: mw, n_positions: 0, n_bases: 0 })
         };
         Ok(BatchPacker { ctx: c.ctx, bufs: [mk()?, mk()?], next: 0, min_baseq })
     }
@@ -294,6 +309,11 @@ impl BatchPacker {
         }, self.ctx)?;
         b.n_positions = out;
         b.n_bases = if n_reads > 0 { offsets[n_reads] - offsets[0] } else { 0 };
+        let mut used = 0usize;
+        check(unsafe {
+            sys::dkb_mask_to_zero_list(b.mask1, out, b.zoff, b.zbytes, b.zbytes_cap, &mut used)
+        }, self.ctx)?;
+        b.zbytes_used = used;
         Ok(b)
     }
 }
@@ -305,6 +325,8 @@ impl Drop for BatchPacker {
             unsafe {
                 sys::dkb_host_free(ptr::null_mut(), b.bases2 as *mut c_void);
                 sys::dkb_host_free(ptr::null_mut(), b.mask1 as *mut c_void);
+                sys::dkb_host_free(ptr::null_mut(), b.zoff as *mut c_void);
+                sys::dkb_host_free(ptr::null_mut(), b.zbytes as *mut c_void);
             }
         }
     }
