@@ -133,6 +133,94 @@ static void pack_range(const uint8_t *seq, const uint8_t *qual, const uint64_t *
   if (p1 & 31) mask1[p1 >> 5] = cur_m;
 }
 
+// ---- the same range, 32 bases at a time (AVX2 + BMI2; chosen at run time) ------------------
+// The output words of the range are zero when this is called; every chunk is OR-ed in at its
+// bit position.  The last 64 positions of a range - where a 64-bit OR could touch the next
+// range's words - and the ends of reads go through the same OR-ing one base at a time.
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#define DKB_HAVE_SIMD_PACK 1
+
+__attribute__((target("avx2,bmi2"))) static void pack_range_avx2(
+    const uint8_t *seq, const uint8_t *qual, const uint64_t *offsets, size_t n_reads, int min_baseq,
+    uint32_t *bases2, uint32_t *mask1, uint64_t p0, uint64_t p1) {
+  const uint64_t o0 = offsets[0];
+  size_t lo = 0, hi = n_reads;
+  while (hi - lo > 1) {
+    const size_t mid = (lo + hi) / 2;
+    if (offsets[mid] - o0 + mid <= p0) lo = mid; else hi = mid;
+  }
+  uint8_t *bb = reinterpret_cast<uint8_t *>(bases2), *mb = reinterpret_cast<uint8_t *>(mask1);
+  const __m256i lower = _mm256_set1_epi8(0x20), cA = _mm256_set1_epi8('a'), cC = _mm256_set1_epi8('c'),
+                cG = _mm256_set1_epi8('g'), cT = _mm256_set1_epi8('t'), one = _mm256_set1_epi8(1),
+                two = _mm256_set1_epi8(2), three = _mm256_set1_epi8(3);
+  const int mq = min_baseq < 0 ? 0 : min_baseq > 255 ? 255 : min_baseq;
+  const __m256i thr = _mm256_set1_epi8((char)mq);
+  const bool never = qual && min_baseq > 255;  // no quality byte can reach the threshold
+  for (size_t r = lo; r < n_reads; r++) {
+    const uint64_t start = offsets[r] - o0 + r, len = offsets[r + 1] - offsets[r];
+    if (start >= p1) break;
+    uint64_t i = p0 > start ? p0 - start : 0;                    // first base of the read inside the range
+    const uint64_t end = start + len < p1 ? len : p1 - start;    // one past its last base inside the range
+    const uint8_t *sp = seq + offsets[r];
+    const uint8_t *qp = qual ? qual + offsets[r] : nullptr;
+    // whole chunks of 32 bases, as long as their 64-bit ORs stay inside this range's words
+    while (i + 32 <= end && start + i + 32 + 64 <= p1 && !never) {
+      __m256i s = _mm256_or_si256(_mm256_loadu_si256(reinterpret_cast<const __m256i *>(sp + i)), lower);
+      const __m256i isA = _mm256_cmpeq_epi8(s, cA), isC = _mm256_cmpeq_epi8(s, cC),
+                    isG = _mm256_cmpeq_epi8(s, cG), isT = _mm256_cmpeq_epi8(s, cT);
+      __m256i ok = _mm256_or_si256(_mm256_or_si256(isA, isC), _mm256_or_si256(isG, isT));
+      if (qp) {
+        const __m256i q = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(qp + i));
+        ok = _mm256_and_si256(ok, _mm256_cmpeq_epi8(_mm256_max_epu8(q, thr), q));  // q >= threshold, unsigned
+      }
+      __m256i code = _mm256_or_si256(_mm256_or_si256(_mm256_and_si256(isC, one), _mm256_and_si256(isG, two)),
+                                     _mm256_and_si256(isT, three));
+      code = _mm256_and_si256(code, ok);
+      const uint32_t m = (uint32_t)_mm256_movemask_epi8(ok);
+      alignas(32) uint64_t lanes[4];
+      _mm256_store_si256(reinterpret_cast<__m256i *>(lanes), code);
+      const uint64_t K = 0x0303030303030303ull;
+      const uint64_t b = _pext_u64(lanes[0], K) | _pext_u64(lanes[1], K) << 16 | _pext_u64(lanes[2], K) << 32 |
+                         _pext_u64(lanes[3], K) << 48;
+      const uint64_t p = start + i;
+      // bases: 64 bits at bit 2p; flags: 32 bits at bit p (byte-granular unaligned ORs)
+      {
+        const uint64_t bit = 2 * p;
+        uint8_t *d = bb + (bit >> 3);
+        const unsigned sh = (unsigned)(bit & 7);  // 0, 2, 4 or 6
+        uint64_t w0, w1 = 0;
+        memcpy(&w0, d, 8);
+        w0 |= b << sh;
+        memcpy(d, &w0, 8);
+        if (sh) {
+          memcpy(&w1, d + 8, 1);
+          w1 |= b >> (64 - sh);
+          memcpy(d + 8, &w1, 1);
+        }
+      }
+      {
+        uint8_t *d = mb + (p >> 3);
+        const unsigned sh = (unsigned)(p & 7);
+        uint64_t w;
+        memcpy(&w, d, 8);
+        w |= (uint64_t)m << sh;
+        memcpy(d, &w, 8);
+      }
+      i += 32;
+    }
+    for (; i < end; i++) {  // what is left of the read in this range, one base at a time
+      const uint32_t c = LUT.t[sp[i]];
+      const uint32_t ok = (c <= 3) & (!qp || (int)qp[i] >= min_baseq);
+      const uint64_t p = start + i;
+      bases2[p >> 4] |= (ok ? c : 0u) << (2 * (p & 15));
+      mask1[p >> 5] |= ok << (p & 31);
+    }
+    // (the separator after the read keeps its zero flag)
+  }
+}
+#endif
+
 int dkb_pack_reads(const uint8_t *seq, const uint8_t *qual, const uint64_t *offsets,
                    size_t n_reads, int min_baseq, uint32_t *bases2, uint32_t *mask1,
                    uint64_t *n_positions_out) {
@@ -143,6 +231,11 @@ int dkb_pack_reads(const uint8_t *seq, const uint8_t *qual, const uint64_t *offs
     if (offsets[r + 1] < offsets[r]) return DKB_EINVAL;
   const uint64_t n_pos = dkb_stream_positions(offsets, n_reads);
   const size_t bw = dkb_stream_bases_words(n_pos), mw = dkb_stream_mask_words(n_pos);
+  bool simd = false;
+#ifdef DKB_HAVE_SIMD_PACK
+  simd = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2") && !getenv("DKB_PACK_SCALAR");
+#endif
+  (void)simd;
   // output words are split between threads on 128-position boundaries: no sharing
   unsigned n_thr = std::thread::hardware_concurrency();
   if (n_thr > 32) n_thr = 32;
@@ -156,7 +249,12 @@ int dkb_pack_reads(const uint8_t *seq, const uint8_t *qual, const uint64_t *offs
     const size_t m0 = (size_t)(p0 / 32), m1 = t + 1 == n_thr ? mw : (size_t)((p0 + per) / 32);
     if (b0 < bw) memset(bases2 + b0, 0, ((b1 < bw ? b1 : bw) - b0) * 4);
     if (m0 < mw) memset(mask1 + m0, 0, ((m1 < mw ? m1 : mw) - m0) * 4);
-    if (p0 < p1 && n_reads) pack_range(seq, qual, offsets, n_reads, min_baseq, bases2, mask1, p0, p1);
+    if (p0 < p1 && n_reads) {
+#ifdef DKB_HAVE_SIMD_PACK
+      if (simd) return pack_range_avx2(seq, qual, offsets, n_reads, min_baseq, bases2, mask1, p0, p1);
+#endif
+      pack_range(seq, qual, offsets, n_reads, min_baseq, bases2, mask1, p0, p1);
+    }
   };
   if (n_thr == 1) {
     work(0);
