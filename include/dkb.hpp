@@ -115,6 +115,35 @@ class Counter {
                                  sample),
           ctx_);
   }
+  // the stream with its flags as a zero list (dkb_mask_to_zero_list): less PCIe traffic;
+  // the vectors must outlive the next sync()
+  struct SparseStream {
+    std::vector<uint32_t> bases2, zoff;
+    std::vector<uint8_t> zbytes;
+    uint64_t n_positions = 0;
+  };
+  static SparseStream to_sparse(const Stream &s) {
+    SparseStream z;
+    z.bases2 = s.bases2;
+    z.n_positions = s.n_positions;
+    z.zoff.resize(dkb_zero_list_blocks(s.n_positions) + 1);
+    size_t used = 0;
+    check(dkb_mask_to_zero_list(s.mask1.data(), s.n_positions, z.zoff.data(), nullptr, 0, &used));
+    z.zbytes.resize(used + 1);
+    check(dkb_mask_to_zero_list(s.mask1.data(), s.n_positions, z.zoff.data(), z.zbytes.data(), used, &used));
+    z.zbytes.resize(used);
+    return z;
+  }
+  void submit(const SparseStream &z, int sample) {
+    check(dkb_batch_submit_sparse(ctx_, z.bases2.data(), z.zoff.data(), z.zbytes.data(), z.zbytes.size(),
+                                  z.n_positions, sample),
+          ctx_);
+  }
+  // multi-GPU: one context per GPU and rank; id from dkb_comm_unique_id on rank 0
+  void comm_init(const void *id, int rank, int world) { check(dkb_comm_init(ctx_, id, rank, world), ctx_); }
+  void counts_allreduce() { check(dkb_counts_allreduce(ctx_), ctx_); }
+  void reduce_push(const dkb_thresholds &t) { check(dkb_reduce_push(ctx_, &t), ctx_); }
+  void reduce_flush(const dkb_thresholds &t) { check(dkb_reduce_flush(ctx_, &t), ctx_); }
   void sync() { check(dkb_sync(ctx_), ctx_); }
   void reset_counts() { check(dkb_counts_reset(ctx_), ctx_); }
   std::vector<uint32_t> entry_counts() {  // [3 samples][n_entries]

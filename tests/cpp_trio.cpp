@@ -29,6 +29,16 @@ int main() {
       if (counts[i] != 1) return 4;
     Results r = c.finalise({1, 1, 0, 0});
     if (r.hits[0] != 8 || r.hits[3] != 8 || r.calls[0] != DKB_CALL_DENOVO) return 5;
+    // the same reads with the flags as a zero list, into the mother's counters; no communicator:
+    // the overlapped reduction runs without NCCL and must equal plain finalise
+    Counter::SparseStream z = Counter::to_sparse(s);
+    if (z.zbytes.size() != 2) return 7;  // two separators, nothing else unusable
+    c.submit(z, 1);
+    c.reduce_push({1, 1, 0, 0});
+    c.reduce_flush({1, 1, 0, 0});
+    std::vector<uint32_t> both = c.entry_counts();
+    for (size_t i = 0; i < e.keys.size(); i++)
+      if (both[i] != 1 || both[e.keys.size() + i] != 1) return 8;
     std::puts("gpu-ok");
   } catch (const Error &err) {
     if (err.code != DKB_ENODEV) {
