@@ -271,7 +271,7 @@ __global__ void k_assign_seeds(const BuildParams B, int pass, uint32_t *set, uin
       if (T.n_probe) probe_insert(T, seed);
       uint32_t h = seed * seed_mult;
       if (pre_words) {  // one-bit pre-filter; the main filter behind it uses an independent hash
-        atomicOr(pre + bloom_word(h, pre_words), 1u << (seed & 31));
+        atomicOr(pre + bloom_word(h, pre_words), 1u << ((uint32_t)((uint64_t)h * pre_words) >> 27));
         h *= PRE_REHASH;
       }
       atomicOr(bloom + bloom_word(h, bloom_words), bloom_bits(seed, h, bloom_words, n_hashes));

@@ -578,13 +578,17 @@ struct ScanWarp {
         x[i] = seed_canon(xr[i] & P.seed_mask, P.cshift, flip);
       }
     }
-    uint32_t h[N], w1[N];
+    uint32_t h[N], w1[N], s1[N];
     if constexpr (PRE) {
 #pragma unroll
       for (int i = 0; i < N; i++) {
         h[i] = x[i] * mult;
         unsigned long long p1;
         asm("mul.wide.u32 %0, %1, %2;" : "=l"(p1) : "r"(h[i]), "r"(P.pre_words));
+        // the bit inside the word comes from the hash too (top of the product's low half): the
+        // raw low bits of a CANONICAL seed are skewed, and reads skew the same way - taking them
+        // as the bit index let 49 % of the lookups through instead of the 41 % the fill predicts
+        s1[i] = (uint32_t)p1 >> 27;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1[i]) : "r"((uint32_t)(p1 >> 32) * P.four + fbase));
       }
     }
@@ -597,8 +601,7 @@ struct ScanWarp {
       lo[i] = (uint32_t)prod;
       word[i] = 0;
       bool pass = true;
-      // pre-filter: bit (s-mer & 31) of the word (the funnel shift wraps its shift amount)
-      if constexpr (PRE) pass = (__funnelshift_r(w1[i], 0, x[i]) & 1u) != 0;
+      if constexpr (PRE) pass = (__funnelshift_r(w1[i], 0, s1[i]) & 1u) != 0;
       // address = base + 4 * word index as ONE wide multiply-add
       unsigned long long ga;
       asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(ga) : "r"((uint32_t)(prod >> 32)), "l"(P.bloom));
