@@ -162,12 +162,12 @@ uint32_t l2_filter_words(double seeds) {
   if (w < BLOOM_WORDS) w = BLOOM_WORDS;
   return (uint32_t)w;
 }
-// Shared-memory pre-filter of the L2 filter mode: 139 KB - with the 24 KB of lists and the
+// Shared-memory pre-filter of the L2 filter mode: 145 KB - with the 18 KB of lists and the
 // 1 KB the system reserves it fills the 164 KB shared-memory carve-out exactly and leaves
 // 92 KB of L1, whose lines track the outstanding L2 loads.  Measured on configs[1]
 // (Tbases/s; profiles/README.md): 107 KB (132 KB carve-out) 4.64, 128 KB 4.91, 139 KB 5.04,
 // 171 KB (196 KB carve-out, 60 KB of L1) 4.94, 192 KB 2.8.
-constexpr uint32_t PRE_WORDS = 35584;
+constexpr uint32_t PRE_WORDS = 37120;
 
 // Words of the pre-filter the build should use for this table (0 = none).  DKB_PREFILTER_WORDS overrides.
 uint32_t pre_filter_words(bool want) {
@@ -389,7 +389,8 @@ int launch_scan(dkb_ctx *ctx, int n_seg, const uint32_t *const *d_bases, const u
   P.prof = ctx->d_prof;
   scan_fn fn = pick_scan(ctx->D, ctx->NH, ctx->gf ? (ctx->pre_words ? 2 : 1) : 0, ctx->prof);
   if (!fn) return fail(ctx, DKB_EINVAL, "no scan kernel for this tuning");
-  size_t smem_bytes = ctx->gf ? SCAN_SMEM_BYTES_GF + (size_t)ctx->pre_words * 4 : SCAN_SMEM_BYTES;
+  size_t smem_bytes = !ctx->gf ? SCAN_SMEM_BYTES
+                      : ctx->pre_words ? SCAN_SMEM_BYTES_PRE + (size_t)ctx->pre_words * 4 : SCAN_SMEM_BYTES_GF;
   if (ctx->D >= 8) smem_bytes += SCAN_TMA_BYTES;  // TMA builds: the per-warp stream ring of the macro path
   {
     std::lock_guard<std::mutex> lk(g_smem_mu);

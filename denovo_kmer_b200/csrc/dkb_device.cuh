@@ -19,14 +19,19 @@ constexpr int WTILE_WORDS = WTILE / 16;    // 128 uint32 words of bases per warp
 #endif
 // 202 KB seed filter resident in shared memory (136 KB in TMA builds, whose stream ring needs 66 KB)
 constexpr int BLOOM_WORDS = DKB_STREAM_LD == 2 ? 34816 : 51712;
-constexpr int HL_CAP = 128;                // per-warp list of filter-hit ids of one tile
+// per-warp list of the filter-hit ids of one (macro) tile; denser tiles take several passes.
+// Behind the pre-filter (mode 2) a macro tile has a handful of hits: 32 ids do, and the 6 KB go
+// to the pre-filter instead (configs[1] 7.09 -> 7.23 Tbases/s; k = 21 at stride 8 4.14 -> 4.04).
+constexpr int HL_CAP_WIDE = 128, HL_CAP_PRE = 32;
+__host__ __device__ constexpr int hl_cap(int fm) { return fm == 2 ? HL_CAP_PRE : HL_CAP_WIDE; }
 constexpr int CQ_CAP = 64;                 // per-warp ring of verified seeds
-constexpr size_t SCAN_LISTS_BYTES = (size_t)SCAN_WARPS * CQ_CAP * 8 + (size_t)SCAN_WARPS * HL_CAP * 2;
-constexpr size_t SCAN_SMEM_BYTES = (size_t)BLOOM_WORDS * 4 + SCAN_LISTS_BYTES;
+constexpr size_t scan_lists_bytes(int fm) { return (size_t)SCAN_WARPS * CQ_CAP * 8 + (size_t)SCAN_WARPS * hl_cap(fm) * 2; }
+constexpr size_t SCAN_SMEM_BYTES = (size_t)BLOOM_WORDS * 4 + scan_lists_bytes(0);
 // L2 filter mode keeps only the lists in shared memory: the rest of the 256 KB stays L1, whose
 // lines are what outstanding global loads are tracked in (a 30 KB L1 caps an SM at ~0.3
 // random loads per clock against 1.0 with a large one: scripts/micro/l2_gather.cu).
-constexpr size_t SCAN_SMEM_BYTES_GF = SCAN_LISTS_BYTES;
+constexpr size_t SCAN_SMEM_BYTES_GF = scan_lists_bytes(1);       // L2 filter, no pre-filter
+constexpr size_t SCAN_SMEM_BYTES_PRE = scan_lists_bytes(2);      // + pre_words * 4
 
 // DKB_STREAM_LD: how the macro path (strides 8, 16) reads the base stream.
 //   0  read-only loads at normal L2 priority        3  evict-first loads

@@ -30,6 +30,7 @@ namespace dkb {
 template <int D, int NH, int FM, bool PROF>
 struct ScanWarp {
   static constexpr bool GF = FM > 0, PRE = FM == 2;
+  static constexpr int HL_CAP = hl_cap(FM);
   static constexpr bool CANON = canon_for_mode(FM);  // seeds keyed by min(s-mer, its reverse complement)
   // Strides 8 and 16 leave 8 / 4 lookups per lane in a 2048-position tile; SUB such tiles
   // form a macro tile with 32 lookups per lane so that hit handling and loop overhead are
@@ -813,6 +814,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
   }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int HL_CAP = hl_cap(FM);
   ScanWarp<D, NH, FM, PROF> W(P, filt, hl_all + warp * HL_CAP, cq_all + warp * CQ_CAP, lane);
 
   const uint32_t n_warps = gridDim.x * SCAN_WARPS;

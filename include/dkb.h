@@ -87,8 +87,8 @@ typedef struct dkb_tuning {
   int stride;       /* D: probe every D-th stream position (1, 2, 4, 8 or 16); 0 = auto */
   int bloom_hashes; /* 1..4 bits per seed in the seed filter; 0 = auto */
   int filter_mode;  /* 1 = filter in shared memory (small candidate sets), 2 = filter in L2
-                       (strides 2..16, 1..2 hashes; the library decides whether a 139 KB
-                       (35 584-word) shared-memory pre-filter goes in front of it, env
+                       (strides 2..16, 1..2 hashes; the library decides whether a 145 KB
+                       (37 120-word) shared-memory pre-filter goes in front of it, env
                        DKB_PREFILTER_WORDS overrides); 0 = auto */
 } dkb_tuning;
 

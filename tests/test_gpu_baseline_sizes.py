@@ -5,7 +5,7 @@ The streams are generated in HBM by the bench's own generator (same seeds as ben
 0), scanned by the CUDA path (auto-tuned, all three samples in one launch), then copied to
 the host and counted by oracle.count_stream — the plain per-position rolling-window walk of
 the packed stream, itself pinned to the per-read oracle by tests/test_oracle.py.
-  configs[1]  64 Mb, 30x, 10 000 candidates, k=31 — must tune to (15, 16, 2, L2) + 35 584-word pre-filter
+  configs[1]  64 Mb, 30x, 10 000 candidates, k=31 — must tune to (15, 16, 2, L2) + 37 120-word pre-filter
   configs[2]  one GPU's shard: 128 Mb of 30x reads, 4 000 local of a 100 000-candidate table
   configs[3]  64 Mb, 100x, 50 000 candidates incl. indels (19.2 Gbases)
   configs[4]  k = 15 / 21 / 25 / 31 on 64 Mb, 30x, 10 000 candidates, base-quality masking on
@@ -80,7 +80,7 @@ def _run(dkb, orc, a, lowq_frac=None):
 
 def test_config1_64mb_30x_10k_full_size(dkb, orc):
     tun, st, calls, variants = _run(dkb, orc, _args())
-    assert tun == (15, 16, 2, 2) and st["prefilter_words"] == 35584, (tun, st["prefilter_words"])
+    assert tun == (15, 16, 2, 2) and st["prefilter_words"] == 37120, (tun, st["prefilter_words"])
     inherited = np.array([v.inherited for v in variants])
     assert (calls[~inherited] & 1).mean() > 0.9 and (calls[inherited] & 1).sum() == 0
 
