@@ -357,15 +357,21 @@ class Job:
     def roofline(self, s0, s1, steps, traffic_key):
         launches = s1["scan_launches_timed"] - s0["scan_launches_timed"]
         scan_ms = (s1["scan_ms_total"] - s0["scan_ms_total"]) / max(launches, 1)
-        bytes_per_launch = self.stream_bytes / max(launches / max(steps, 1), 1)
+        # what the kernel must stream: the 2-bit bases, and - when its lookups are gated by the
+        # flags (dkb_stats.gated_lookups) - the 1-bit flag stream as well
+        gated = bool(s1.get("gated_lookups", 0))
+        per_step = self.stream_bytes + (self.mask_bytes if gated else 0)
+        bytes_per_launch = per_step / max(launches / max(steps, 1), 1)
         peak, peak_src = measured_peak_gbs()
         achieved = bytes_per_launch / (scan_ms * 1e-3) / 1e9
         return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": profile_traffic(traffic_key), "kernel": "dkb::k_scan",
                 "peak_source": peak_src, "launch_ms": scan_ms, "bytes_per_launch": bytes_per_launch,
-                "launches_per_step": launches / max(steps, 1),
-                "note": "bytes = 2-bit base stream only (0.2517 B/read base incl. separators), all three samples "
-                        "of the step in one launch; the 1-bit mask stream is read only for verified seed hits"}
+                "launches_per_step": launches / max(steps, 1), "gated_lookups": gated,
+                "note": ("bytes = 2-bit base stream + 1-bit flag stream (0.3775 B/read base incl. separators): the "
+                         "kernel reads both in full (lookups gated by the flags)" if gated else
+                         "bytes = 2-bit base stream only (0.2517 B/read base incl. separators); the 1-bit flag "
+                         "stream is read only for verified seed hits") + "; all three samples of the step in one launch"}
 
     def close(self):
         self.kc.close()
@@ -594,7 +600,7 @@ def run_ours(a):
                     (job.stream_bytes + job.mask_bytes) / 1e9),
                 "table_entries": int(st["n_entries"]), "seeds": int(st["n_seeds"]),
                 "tuning_seedlen_stride_hashes_filtermode": list(kc.tuning()),
-                "prefilter_words": int(st.get("prefilter_words", 0)),
+                "prefilter_words": int(st.get("prefilter_words", 0)), "gated_lookups": bool(st.get("gated_lookups", 0)),
                 "denovo_calls": int((calls & 1).sum()), "variants": int(len(calls)),
                 "collective": ("1 ncclAllReduce(sum) of %d uint32 per step inside libdkb.so (dkb_reduce_push); "
                                "communicator of %d ranks, NCCL %d" % (3 * len(job.entries), comm[1], comm[2]))

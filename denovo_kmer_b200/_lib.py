@@ -32,7 +32,8 @@ class Stats(C.Structure):
         "n_entries", "n_live_entries", "table_slots", "n_seeds", "seed_slots", "bloom_words",
         "bloom_bits_set", "scan_launches", "positions_scanned", "bloom_hits", "seed_hits",
         "windows_probed", "window_hits", "scan_launches_timed")] + [
-        ("scan_ms_total", C.c_double), ("last_scan_ms", C.c_float), ("prefilter_words", C.c_uint32)]
+        ("scan_ms_total", C.c_double), ("last_scan_ms", C.c_float), ("prefilter_words", C.c_uint32),
+        ("gated_lookups", C.c_uint32)]
 
 
 # every symbol include/dkb.h declares: (restype, argtypes)

@@ -34,6 +34,7 @@ struct dkb_ctx {
   dkb_tuning user_tuning{0, 0, 0, 0};
   int s = 0, D = 0, NH = 0;  // resolved at table build
   bool gf = false;           // seed filter probed in L2 instead of shared memory
+  bool gate = false;         // stage A reads the flags and skips lookups of unusable seeds (modes 3, 4)
   uint32_t bloom_words = BLOOM_WORDS;
 
   // entries
@@ -217,8 +218,13 @@ double tile_cost(double n_entries, bool hints, int k, int s, int D, int NH, bool
   const double chance = seeds / pow(4.0, s);  // P(random s-mer is a seed)
   const double table = seeds > 2e6 ? 3.0 : seeds > 5e5 ? 1.3 : 1.0;
   const double chance_cost = 25.0 * table * lookups_tile * chance;
-  double l2_lookup = 119.0;
-  if (pre) l2_lookup = 22.0 + 105.0 * (1.0 - exp(-seeds / (32.0 * pre_filter_words(true))));
+  // (strides 8, 16: lookups gated by the flag stream cost ~8 more and reach the filter 0.58 times
+  // as often at the usual 4 % of unusable positions; they are used when that pays - see the build)
+  double l2_lookup = D >= 8 ? 8.0 + 0.58 * 119.0 : 119.0;
+  if (pre) {
+    const double pass = 1.0 - exp(-seeds / (32.0 * pre_filter_words(true)));
+    l2_lookup = D >= 8 && pass > 0.55 ? 30.0 + 0.58 * 105.0 * pass : 22.0 + 105.0 * pass;
+  }
   if (D >= 8)  // (round-2 refit: the probe array and normal-priority stream loads made the shared-memory mode cheaper)
     return (gf ? 61.0 : 37.0) + lookups_lane * (gf ? l2_lookup : 16.0 + NH) + (gf ? 16.0 : 14.6) * table * hits +
            chance_cost;
@@ -387,7 +393,7 @@ int launch_scan(dkb_ctx *ctx, int n_seg, const uint32_t *const *d_bases, const u
   P.k = ctx->k;
   P.s = ctx->s;
   P.prof = ctx->d_prof;
-  scan_fn fn = pick_scan(ctx->D, ctx->NH, ctx->gf ? (ctx->pre_words ? 2 : 1) : 0, ctx->prof);
+  scan_fn fn = pick_scan(ctx->D, ctx->NH, ctx->gf ? (ctx->pre_words ? 2 : 1) + (ctx->gate ? 2 : 0) : 0, ctx->prof);
   if (!fn) return fail(ctx, DKB_EINVAL, "no scan kernel for this tuning");
   size_t smem_bytes = !ctx->gf ? SCAN_SMEM_BYTES
                       : ctx->pre_words ? SCAN_SMEM_BYTES_PRE + (size_t)ctx->pre_words * 4 : SCAN_SMEM_BYTES_GF;
@@ -824,6 +830,16 @@ int dkb_table_build(dkb_ctx *ctx, const uint64_t *keys, const uint32_t *variant_
     CU(cudaMalloc(&ctx->d_bloom, (size_t)ctx->bloom_words * 4));
     CU(cudaMemsetAsync(ctx->d_bloom, 0, (size_t)ctx->bloom_words * 4, st));
     ctx->pre_words = ctx->gf ? pre_filter_words(ctx->want_pre) : 0;
+    // Gated lookups (macro path of the L2 modes): worth their instructions when most lookups
+    // end in an L2 gather - always without a pre-filter, behind one when it passes more than
+    // about half (measured, profiles/README.md: 10 000 candidates, 40 % passed: 7.15 -> 6.45
+    // Tbases/s; 14 000, 51 %: 5.78 -> 5.83; 20 000, 64 %: 4.52 -> 5.02; no pre-filter: 3.91 -> 6.23).
+    ctx->gate = false;
+    if (ctx->gf && ctx->D >= 8) {
+      const double pass = ctx->pre_words ? 1.0 - exp(-(double)n_seeds / (32.0 * ctx->pre_words)) : 1.0;
+      ctx->gate = pass > 0.55;
+      if (const char *e = getenv("DKB_GATE")) ctx->gate = atoi(e) != 0;
+    }
     if (ctx->pre_words) {
       CU(cudaMalloc(&ctx->d_pre, (size_t)ctx->pre_words * 4));
       CU(cudaMemsetAsync(ctx->d_pre, 0, (size_t)ctx->pre_words * 4, st));
@@ -1272,6 +1288,7 @@ int dkb_stats_get(dkb_ctx *ctx, dkb_stats *out) {
   out->scan_ms_total = ctx->scan_ms_total;
   out->last_scan_ms = ctx->last_scan_ms;
   out->prefilter_words = ctx->gf ? ctx->pre_words : 0;
+  out->gated_lookups = ctx->gate ? 1u : 0u;
   return DKB_OK;
 }
 

@@ -23,7 +23,14 @@ constexpr int BLOOM_WORDS = DKB_STREAM_LD == 2 ? 34816 : 51712;
 // Behind the pre-filter (mode 2) a macro tile has a handful of hits: 32 ids do, and the 6 KB go
 // to the pre-filter instead (configs[1] 7.09 -> 7.23 Tbases/s; k = 21 at stride 8 4.14 -> 4.04).
 constexpr int HL_CAP_WIDE = 128, HL_CAP_PRE = 32;
-__host__ __device__ constexpr int hl_cap(int fm) { return fm == 2 ? HL_CAP_PRE : HL_CAP_WIDE; }
+// Filter modes of the scan kernel (template parameter FM):
+//   0 seed filter in shared memory      1 in L2      2 in L2 behind the shared-memory pre-filter
+//   3, 4 = 1, 2 with GATED lookups: stage A also reads the flag stream and skips every lookup
+//   whose seed holds an unusable base (no countable window can contain such a seed).  Saves the
+//   lookup's load-path work, costs instructions: pays where the gathers bound the kernel.
+__host__ __device__ constexpr bool fm_pre(int fm) { return fm == 2 || fm == 4; }
+__host__ __device__ constexpr bool fm_gate(int fm) { return fm >= 3; }
+__host__ __device__ constexpr int hl_cap(int fm) { return fm_pre(fm) ? HL_CAP_PRE : HL_CAP_WIDE; }
 constexpr int CQ_CAP = 64;                 // per-warp ring of verified seeds
 constexpr size_t scan_lists_bytes(int fm) { return (size_t)SCAN_WARPS * CQ_CAP * 8 + (size_t)SCAN_WARPS * hl_cap(fm) * 2; }
 constexpr size_t SCAN_SMEM_BYTES = (size_t)BLOOM_WORDS * 4 + scan_lists_bytes(0);

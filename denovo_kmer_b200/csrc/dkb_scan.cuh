@@ -25,11 +25,11 @@
 
 namespace dkb {
 
-// FM = filter mode: 0 seed filter in shared memory, 1 in L2, 2 in L2 behind a one-bit
-// shared-memory pre-filter.
+// FM = filter mode (dkb_device.cuh): 0 seed filter in shared memory, 1 in L2, 2 in L2 behind a
+// one-bit shared-memory pre-filter, 3 / 4 = 1 / 2 with gated lookups.
 template <int D, int NH, int FM, bool PROF>
 struct ScanWarp {
-  static constexpr bool GF = FM > 0, PRE = FM == 2;
+  static constexpr bool GF = FM > 0, PRE = fm_pre(FM), GATE = fm_gate(FM);
   static constexpr int HL_CAP = hl_cap(FM);
   static constexpr bool CANON = canon_for_mode(FM);  // seeds keyed by min(s-mer, its reverse complement)
   // Strides 8 and 16 leave 8 / 4 lookups per lane in a 2048-position tile; SUB such tiles
@@ -48,11 +48,7 @@ struct ScanWarp {
   uint32_t ch = 0, ct = 0;
   int lane;
   uint32_t lt_mask;
-#ifndef DKB_TABLE_POLICY
-#define DKB_TABLE_POLICY 0  // experiment: 0 evict-last for every table load, 1 normal for slot/key/probe loads
-#endif
-  uint64_t keep = l2_policy_evict_last();  // cache policy of the filter loads ...
-  uint64_t keep_t = DKB_TABLE_POLICY == 0 ? l2_policy_evict_last() : l2_policy_normal();  // ... and of the table loads
+  uint64_t keep = l2_policy_evict_last();  // cache policy of every filter and table load
   const uint32_t zero;                     // 0, but not to the compiler
   const uint32_t fbase;                    // shared-memory address of the (pre-)filter
   // stage B probes in flight (issued at the end of one tile, consumed in the next)
@@ -86,7 +82,7 @@ struct ScanWarp {
     uint32_t *const counts = P.seg[cur].counts;
     while (true) {
       const uint4 *bp = P.kt.slots + bk * KBUCKET;
-      const uint4 s0 = ldg_v4_hint(bp, keep_t), s1 = ldg_v4_hint(bp + 1, keep_t);
+      const uint4 s0 = ldg_v4_hint(bp, keep), s1 = ldg_v4_hint(bp + 1, keep);
       const uint64_t k0 = slot_key(s0), k1 = slot_key(s1);
       if (k0 == key && s0.z != ENTRY_DEAD && slot_offset(s0.w, ori, j % D, D) == (uint32_t)j) {
         atomicAdd(counts + s0.z, 1u);
@@ -124,7 +120,7 @@ struct ScanWarp {
       // the record for this read orientation: a 32-byte half of the seed's slot (half 0 is
       // the sector stage B already touched)
       const uint4 *rp = P.st.slots + 2 * (size_t)(uint32_t)(e >> 32);  // e >> 32 = 2 * slot + flip
-      const uint4 r0 = ldg_v4_hint(rp, keep_t), r1 = ldg_v4_hint(rp + 1, keep_t);
+      const uint4 r0 = ldg_v4_hint(rp, keep), r1 = ldg_v4_hint(rp + 1, keep);
       const uint32_t nb0 = r0.z, nb1 = r0.w, nb2 = r1.x, wd0 = r1.y, wd1 = r1.z, wd2 = r1.w;
       uint32_t b[5], m[3];
 #pragma unroll
@@ -249,14 +245,14 @@ struct ScanWarp {
   }
   // the word that says whether entry `e` holds a seed (and whether to walk on)
   __device__ __forceinline__ uint32_t ld_slot_word(uint32_t e) const {
-    if (use_probe()) return ldg_u32_hint(P.st.probe + e, keep_t);
-    return ldg_u32_hint(reinterpret_cast<const uint32_t *>(P.st.slots) + 16 * (size_t)e, keep_t);
+    if (use_probe()) return ldg_u32_hint(P.st.probe + e, keep);
+    return ldg_u32_hint(reinterpret_cast<const uint32_t *>(P.st.slots) + 16 * (size_t)e, keep);
   }
   // entry of the structure stage B verified against -> the seed's slot
   __device__ __forceinline__ uint32_t slot_of(uint32_t x, uint32_t e) const {
     if (!use_probe()) return e;
     uint32_t b = seed_home(x, P.st.n_slots);
-    while ((ldg_u32_hint(reinterpret_cast<const uint32_t *>(P.st.slots) + 16 * (size_t)b, keep_t) & ST_SEED_BITS) != x)
+    while ((ldg_u32_hint(reinterpret_cast<const uint32_t *>(P.st.slots) + 16 * (size_t)b, keep) & ST_SEED_BITS) != x)
       b = seed_next(b, P.st.n_slots);
     return b;
   }
@@ -542,7 +538,7 @@ struct ScanWarp {
   // each and overlap; IMAD.WIDE 2.4; a multiply-high 5 and it holds up the ALU pipe, so
   // there is none here.  ALU: cut (caller), index shift, one shift per filter bit, AND.
   // FMA: hash, wide multiply, address, and the caller's accumulate.
-  __device__ __forceinline__ uint32_t lookup(uint32_t x, uint32_t mult) const {
+  __device__ __forceinline__ uint32_t lookup(uint32_t x, uint32_t mult, bool ok = true) const {
     if constexpr (CANON) {
       uint32_t flip;
       x = seed_canon(x & P.seed_mask, P.cshift, flip);
@@ -553,7 +549,8 @@ struct ScanWarp {
     asm("mul.wide.u32 %0, %1, %2;" : "=l"(prod) : "r"(h), "r"(P.filter_words));
     // byte address = idx * 4 + base as a multiply-add (P.four is opaque), not an ALU-pipe LEA
     const uint32_t addr = (uint32_t)(prod >> 32) * P.four + fbase;
-    asm("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(addr));
+    word = 0;
+    if (ok) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(addr));
     const uint32_t lo = (uint32_t)prod;
     uint32_t bit = __funnelshift_r(word, 0, x);  // the shift wraps: bit (x & 31) comes down to bit 0
     if (NH >= 2) bit &= __funnelshift_r(word, 0, lo >> 27);
@@ -567,8 +564,11 @@ struct ScanWarp {
   // lookup at a time, each load's latency was exposed in full: the LDS 30 cycles, the L2 load
   // 300+, per lookup and warp).  x[i] = the s-mer of lookup first + i; returns a with the hit
   // bits added at bit positions top - (first + i).
+  // ok bit i = the seed of lookup i holds only usable bases (stage A reads the flag stream for
+  // this): a seed with an N, a low-quality base or a read separator inside cannot belong to a
+  // countable window, so its lookup - the LDS and the L2 gather - is skipped.
   template <int N>
-  __device__ __forceinline__ uint32_t gf_lookups(const uint32_t (&xr)[N], uint32_t a, int top) const {
+  __device__ __forceinline__ uint32_t gf_lookups(const uint32_t (&xr)[N], uint32_t ok, uint32_t a, int top) const {
     const uint32_t mult = P.seed_mult;
     uint32_t x[N];
 #pragma unroll
@@ -590,7 +590,9 @@ struct ScanWarp {
         // raw low bits of a CANONICAL seed are skewed, and reads skew the same way - taking them
         // as the bit index let 49 % of the lookups through instead of the 41 % the fill predicts
         s1[i] = (uint32_t)p1 >> 27;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1[i]) : "r"((uint32_t)(p1 >> 32) * P.four + fbase));
+        w1[i] = 0;
+        if ((ok >> i) & 1u)
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1[i]) : "r"((uint32_t)(p1 >> 32) * P.four + fbase));
       }
     }
     uint32_t word[N], lo[N];
@@ -601,8 +603,8 @@ struct ScanWarp {
       asm("mul.wide.u32 %0, %1, %2;" : "=l"(prod) : "r"(hh), "r"(P.bloom_words));
       lo[i] = (uint32_t)prod;
       word[i] = 0;
-      bool pass = true;
-      if constexpr (PRE) pass = (__funnelshift_r(w1[i], 0, s1[i]) & 1u) != 0;
+      bool pass = (ok >> i) & 1u;
+      if constexpr (PRE) pass = (__funnelshift_r(w1[i], 0, s1[i]) & 1u) != 0;  // (w1 is 0 for a skipped lookup)
       // address = base + 4 * word index as ONE wide multiply-add
       unsigned long long ga;
       asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(ga) : "r"((uint32_t)(prod >> 32)), "l"(P.bloom));
@@ -632,9 +634,31 @@ struct ScanWarp {
   // ---- stage A, macro-tile form: LPT lookups of one sub-tile, hit bits in the low bits,
   // first lookup highest.  At stride 16 every seed lies inside one word (s <= 15): no
   // cut, no halo.
-  __device__ __forceinline__ uint32_t stage_a_sub(const uint32_t (&w)[5]) const {
+  // mk = the flags of the lane's 64 positions.  A seed that runs past them (stride 8, last
+  // lookup of the chunk) is looked up regardless - skipping is only ever an optimisation.
+  __device__ __forceinline__ uint32_t stage_a_sub(const uint32_t (&w)[5], uint2 mk) const {
     const uint32_t mult = P.seed_mult;
+    const uint32_t sbits = (1u << P.s) - 1u;  // s <= 15
     uint32_t a = 0;
+    uint32_t okm = ~0u;  // bit n = the seed of lookup n (at chunk position n * D) is usable throughout
+    if constexpr (GATE && D == 16) {
+      // two seeds per flag word (bits 0..s-1 and 16..16+s-1): all ones + 1 carries into bit s
+      const uint32_t sel = sbits | sbits << 16;
+      const uint32_t u0 = ((mk.x & sel) + 0x00010001u) >> P.s, u1 = ((mk.y & sel) + 0x00010001u) >> P.s;
+      okm = (u0 & 1u) | (u0 >> 15 & 2u) | (u1 & 1u) << 2 | (u1 >> 13 & 8u);
+    } else if constexpr (GATE) {
+      okm = 0;
+#pragma unroll
+      for (int n = 0; n < LPT; n++) {
+        const int pos = n * D;  // 0 .. 63
+        uint32_t f;
+        if (pos + 15 <= 32) f = mk.x >> pos;
+        else if (pos >= 32 && pos + 15 <= 64) f = mk.y >> (pos - 32);
+        else if (pos < 32) f = __funnelshift_r(mk.x, mk.y, pos);
+        else f = mk.y >> (pos - 32) | ~0u << (64 - pos);  // the part beyond the chunk counts as usable
+        okm |= (uint32_t)((f & sbits) == sbits) << n;
+      }
+    }
     if constexpr (GF) {
       constexpr int PERW = 16 / D;  // lookups per word (1 or 2)
 #pragma unroll
@@ -645,7 +669,7 @@ struct ScanWarp {
           const int c = c0 + i / PERW, t = (i % PERW) * D;
           x[i] = t ? __funnelshift_r(w[c], w[c + 1], 2 * t) : w[c];
         }
-        a = gf_lookups<4>(x, a, LPT - 1 - c0 * PERW);
+        a = gf_lookups<4>(x, okm >> (c0 * PERW), a, LPT - 1 - c0 * PERW);
       }
       return a;
     }
@@ -655,7 +679,7 @@ struct ScanWarp {
 #pragma unroll
       for (int t = 0; t < 16; t += D, n++) {
         const uint32_t x = t ? __funnelshift_r(w[c], w[c + 1], 2 * t) : w[c];
-        a = mad_pw(lookup(x, mult), LPT - 1 - n, a);
+        a = mad_pw(lookup(x, mult, (okm >> n) & 1u), LPT - 1 - n, a);
       }
     }
     return a;
@@ -685,7 +709,7 @@ struct ScanWarp {
             const int t = t0 + i * D;
             x[i] = t ? __funnelshift_r(w[c], w[c + 1], 2 * t) : w[c];
           }
-          a = gf_lookups<4>(x, a, 31 - ((c * NB + t0 / D) & 31));
+          a = gf_lookups<4>(x, 0xFu, a, 31 - ((c * NB + t0 / D) & 31));
         }
       } else {
 #pragma unroll
@@ -842,9 +866,27 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
       const uint32_t e = (t0 + GS) * WTILE_WORDS;
       edge = HALO && e < S.n_bwords ? S.bases[e] : 0u;
     };
+    // the flags of the lane's chunks in the group's sub-tiles: two words (64 positions) each
+    constexpr bool GATE = fm_gate(FM);
+    auto load_flags = [&](const ScanSegment &S, uint32_t t0, uint2 (&mk)[GS]) {
+#pragma unroll
+      for (int j = 0; j < GS; j++) {
+        if constexpr (!GATE) {
+          mk[j] = make_uint2(~0u, ~0u);
+          continue;
+        }
+        const uint32_t mi = (t0 + j) * (WTILE / 32) + lane * 2;
+        if (mi + 2 <= S.n_mwords) {
+          mk[j] = __ldcs(reinterpret_cast<const uint2 *>(S.mask + mi));
+        } else {
+          mk[j].x = mi < S.n_mwords ? S.mask[mi] : 0u;
+          mk[j].y = 0u;
+        }
+      }
+    };
     // stage A of one group +, after the last group of a macro tile, its hit handling
     uint32_t acc = 0;
-    auto filter_group = [&](const uint4 (&v)[GS], uint32_t edge) {
+    auto filter_group = [&](const uint4 (&v)[GS], uint32_t edge, const uint2 (&mk)[GS]) {
 #pragma unroll
       for (int j = 0; j < GS; j++) {
         uint32_t w[5] = {v[j].x, v[j].y, v[j].z, v[j].w, 0};
@@ -856,7 +898,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
                                            : edge;
           w[4] = lane == 31 ? wrap : up;
         }
-        acc = acc << LPT | W.stage_a_sub(w);
+        acc = acc << LPT | W.stage_a_sub(w, mk[j]);
       }
     };
 #if DKB_STREAM_LD == 2
@@ -917,10 +959,12 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
         for (int j = 0; j < GS; j++) v[j] = lds_v4(sa + j * 512 + lane * 16);
         if (HALO) edge = lds_u32(sa + GS * 512);
       }
+      uint2 mk[GS];
+      load_flags(P.seg[cc.u.seg], cc.u.local(P) * SUB + cc.g * GS, mk);
       const uint32_t cur_macro = cc.u.local(P);
       const bool last_group = cc.g == GPM - 1;
       advance(cc);
-      filter_group(v, edge);
+      filter_group(v, edge, mk);
       // the stage's words have been used (stage A depends on them), so it can be refilled
       __syncwarp();
       if (pc.u.live(P)) { issue(st); advance(pc); }
@@ -950,24 +994,34 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) k_scan(const ScanParams P) {
     };
     int g = 0;
     uint4 nxt[GS];
+    uint2 nxt_mk[GS];
     uint32_t nxt_edge = 0;
-    if (c.live(P)) load_group(P.seg[c.seg], c.local(P) * SUB, nxt, nxt_edge);
+    if (c.live(P)) {
+      load_group(P.seg[c.seg], c.local(P) * SUB, nxt, nxt_edge);
+      load_flags(P.seg[c.seg], c.local(P) * SUB, nxt_mk);
+    }
     while (c.live(P)) {
       uint4 v[GS];
+      uint2 mk[GS];
 #pragma unroll
-      for (int j = 0; j < GS; j++) v[j] = nxt[j];
+      for (int j = 0; j < GS; j++) { v[j] = nxt[j]; mk[j] = nxt_mk[j]; }
       const uint32_t edge = nxt_edge;
       const uint32_t cur_macro = c.local(P);
       const bool last_group = g == GPM - 1;
       if (last_group) { c.unit += n_warps; c.settle_seg(P); g = 0; } else { g++; }
-      if (c.live(P)) load_group(P.seg[c.seg], c.local(P) * SUB + g * GS, nxt, nxt_edge);
-      filter_group(v, edge);
+      if (c.live(P)) {
+        load_group(P.seg[c.seg], c.local(P) * SUB + g * GS, nxt, nxt_edge);
+        load_flags(P.seg[c.seg], c.local(P) * SUB + g * GS, nxt_mk);
+      }
+      filter_group(v, edge, mk);
       if (last_group) {
         W.consume_pending(acc);
         // same scoreboard trap as in the tile path: settle the prefetched group first
 #pragma unroll
-        for (int j = 0; j < GS; j++)
+        for (int j = 0; j < GS; j++) {
           asm volatile("" : "+r"(nxt[j].x), "+r"(nxt[j].y), "+r"(nxt[j].z), "+r"(nxt[j].w));
+          asm volatile("" : "+r"(nxt_mk[j].x), "+r"(nxt_mk[j].y));
+        }
         asm volatile("" : "+r"(nxt_edge));
         const uint32_t w0[5] = {0, 0, 0, 0, 0};
 #if DKB_X != 7  // (7: timing / traffic experiment without any hit handling)

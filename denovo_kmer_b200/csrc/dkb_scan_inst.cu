@@ -14,7 +14,8 @@
 namespace dkb {
 typedef void (*scan_fn)(const ScanParams);
 
-// fm: 0 = filter in shared memory, 1 = in L2, 2 = in L2 behind the shared-memory pre-filter
+// fm: 0 = filter in shared memory, 1 = in L2, 2 = in L2 behind the shared-memory pre-filter,
+// 3 / 4 = 1 / 2 with gated lookups (macro path: strides 8 and 16)
 scan_fn DKB_CAT(pick_scan_d, DKB_INST_D)(int NH, int fm, bool prof) {
   constexpr int D = DKB_INST_D;
 #define PICK(h, m)                                                                      \
@@ -24,10 +25,16 @@ scan_fn DKB_CAT(pick_scan_d, DKB_INST_D)(int NH, int fm, bool prof) {
 #if DKB_INST_D >= 2
   PICK(2, 1) PICK(2, 2)
 #endif
+#if DKB_INST_D >= 8
+  PICK(2, 3) PICK(2, 4)
+#endif
 #ifndef DKB_AB_BUILD
   PICK(1, 0) PICK(3, 0) PICK(4, 0)
 #if DKB_INST_D >= 2
   PICK(1, 1) PICK(1, 2)
+#endif
+#if DKB_INST_D >= 8
+  PICK(1, 3) PICK(1, 4)
 #endif
 #endif
 #undef PICK

@@ -257,6 +257,8 @@ typedef struct dkb_stats {
   double scan_ms_total;      /* sum of per-launch CUDA-event times of the scan kernel */
   float last_scan_ms;        /* CUDA-event time of the most recent finished scan kernel */
   uint32_t prefilter_words;  /* L2 filter mode: words of the shared-memory pre-filter, 0 = none */
+  uint32_t gated_lookups;    /* 1: the scan also reads the flag stream in full and skips the lookups of
+                                seeds that hold an unusable base (env DKB_GATE=0/1 overrides) */
 } dkb_stats;
 int dkb_stats_get(dkb_ctx *ctx, dkb_stats *out);
 int dkb_profile_counters(dkb_ctx *ctx, int enable);

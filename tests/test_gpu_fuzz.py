@@ -1,5 +1,5 @@
 """-m gpu: seeded random cases through every degree of freedom at once - k, seed length,
-stride, filter bits, filter mode, pre-filter size, window hints, drop_shared, indels, ragged
+stride, filter bits, filter mode, pre-filter size, gated lookups, window hints, drop_shared, indels, ragged
 reads, N / low-quality rates, batch cuts, one launch per trio or per batch, dense or zero-list
 flags - each against the oracle, bit for bit.  Catches interactions the fixed parity cases
 (tests/test_gpu_parity.py) do not enumerate."""
@@ -25,7 +25,8 @@ def _case(rng):
                 indel=float(rng.choice([0.0, 0.5])), ragged=bool(rng.integers(0, 2)),
                 n_rate=float(rng.choice([0.0, 0.002, 0.02])), lowq=float(rng.choice([0.0, 0.03, 0.2])),
                 batches=int(rng.integers(1, 4)), how=str(rng.choice(["host", "sparse", "multi"])),
-                auto=bool(rng.integers(0, 4) == 0), seed=int(rng.integers(1, 1 << 30)))
+                auto=bool(rng.integers(0, 4) == 0), gate=str(rng.choice(["", "0", "1"])),
+                seed=int(rng.integers(1, 1 << 30)))
 
 
 @pytest.mark.parametrize("case_seed", range(40))
@@ -33,6 +34,8 @@ def test_random_case(dkb, orc, case_seed, monkeypatch):
     c = _case(np.random.default_rng(1000 + case_seed))
     k = c["k"]
     monkeypatch.setenv("DKB_PREFILTER_WORDS", str(c["pre"]))
+    if c["gate"]:
+        monkeypatch.setenv("DKB_GATE", c["gate"])  # lookups gated by the flag stream: forced on / off
     trio = synth.make_trio_host(60_000, 12, 25, k, seed=c["seed"], indel_frac=c["indel"], ragged=c["ragged"],
                                 n_rate=c["n_rate"], lowq_frac=c["lowq"])
     entries = dkb.variant_kmers(trio.variant_tuples(), k, drop_shared=c["drop_shared"])

@@ -29,6 +29,21 @@ def test_snv_trio_k31(dkb, orc, tuning, hints):
     _check(dkb, orc, trio, 31, tuning=tuning, hints=hints)
 
 
+@pytest.mark.parametrize("gate", ["0", "1"])
+@pytest.mark.parametrize("pre_words", [0, 1024, 37120])
+@pytest.mark.parametrize("tuning", [(15, 16, 2, 2), (15, 16, 1, 2), (14, 8, 2, 2), (13, 8, 1, 2), (9, 16, 2, 2)])
+def test_gated_lookups(dkb, orc, tuning, pre_words, gate, monkeypatch):
+    """Strides 8 and 16 of the L2 filter modes with the lookups gated by the flag stream (a seed
+    that holds an N, a low-quality base or a separator is not looked up) forced on and off: the
+    counters are the oracle's either way; heavy masking so that most seeds are affected."""
+    monkeypatch.setenv("DKB_PREFILTER_WORDS", str(pre_words))
+    monkeypatch.setenv("DKB_GATE", gate)
+    trio = synth.make_trio_host(150_000, 14, 30, 31, seed=77, n_rate=0.01, lowq_frac=0.08, ragged=True)
+    _check(dkb, orc, trio, 31, tuning=tuning)
+    trio = synth.make_trio_host(150_000, 14, 30, 31, seed=78, n_rate=0.0, lowq_frac=0.0)
+    _check(dkb, orc, trio, 31, tuning=tuning, hints=False)
+
+
 @pytest.mark.parametrize("pre_words", [0, 64, 1024, 32768, 35584])
 @pytest.mark.parametrize("tuning", [(15, 16, 2, 2), (15, 16, 1, 2), (14, 8, 2, 2), (14, 4, 2, 2), (12, 2, 1, 2)])
 def test_l2_filter_behind_prefilter(dkb, orc, tuning, pre_words, monkeypatch):
