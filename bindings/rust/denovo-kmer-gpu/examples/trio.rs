@@ -27,7 +27,7 @@ pub fn run_trio(device: i32, k: i32, min_baseq: i32, thr: Thresholds, cands: &[C
                 kc.sync()?; // both pinned buffers are in use: wait before repacking one
                 in_flight = 0;
             }
-            let batch = packer.next(&seq, Some(&qual), &off)?;
+            let batch = packer.next(&seq, Some(qual.as_slice()), &off)?;
             kc.submit(batch, sample as i32)?;
             in_flight += 1;
         }

@@ -74,10 +74,11 @@ pub struct Candidate<'a> {
 
 /// `dkb_variant_kmers`: spanning k-mers of every candidate's REF and ALT haplotype.
 pub fn variant_kmers(cands: &[Candidate<'_>], k: i32, drop_shared: bool) -> Result<Entries> {
-    let own = |f: fn(&Candidate<'_>) -> &str| -> Vec<CString> {
-        cands.iter().map(|c| CString::new(f(c)).expect("no NUL in sequence")).collect()
-    };
-    let (l, r, a, t) = (own(|c| c.left), own(|c| c.r#ref), own(|c| c.alt), own(|c| c.right));
+    fn own<'a>(it: impl Iterator<Item = &'a str>) -> Vec<CString> {
+        it.map(|s| CString::new(s).expect("no NUL in sequence")).collect()
+    }
+    let (l, r, a, t) = (own(cands.iter().map(|c| c.left)), own(cands.iter().map(|c| c.r#ref)),
+                        own(cands.iter().map(|c| c.alt)), own(cands.iter().map(|c| c.right)));
     let ptrs = |v: &Vec<CString>| -> Vec<*const c_char> { v.iter().map(|s| s.as_ptr()).collect() };
     let (lp, rp, ap, tp) = (ptrs(&l), ptrs(&r), ptrs(&a), ptrs(&t));
     let mut n: usize = 0;
