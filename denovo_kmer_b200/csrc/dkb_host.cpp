@@ -133,91 +133,143 @@ static void pack_range(const uint8_t *seq, const uint8_t *qual, const uint64_t *
   if (p1 & 31) mask1[p1 >> 5] = cur_m;
 }
 
-// ---- the same range, 32 bases at a time (AVX2 + BMI2; chosen at run time) ------------------
-// The output words of the range are zero when this is called; every chunk is OR-ed in at its
-// bit position.  The last 64 positions of a range - where a 64-bit OR could touch the next
-// range's words - and the ends of reads go through the same OR-ing one base at a time.
+// ---- the same range, 32 or 64 bases at a time (AVX2 / AVX-512 BW, + BMI2; chosen at run time) --
+// A chunk of bases becomes three bit masks - usable = (a|c|g|t) & (qual >= threshold), and the two
+// bit planes (c|t), (g|t) of the 2-bit codes, zero where the base is unusable - and the planes
+// are interleaved into stream bits with two bit deposits per 32 bases.  The range's positions are
+// produced strictly in order through two bit writers that keep the unfinished word in a register
+// and store every 64-bit word exactly once: OR-ing chunks into memory at arbitrary bit offsets
+// instead made each chunk's load wait for the previous chunk's narrower store (no store
+// forwarding) and ran at a third of this speed.
 #if defined(__x86_64__) && defined(__GNUC__)
 #include <immintrin.h>
 #define DKB_HAVE_SIMD_PACK 1
 
+extern "C++" {  // (templates; this part of the file sits inside extern "C")
+namespace {
+struct BitWriter {
+  uint8_t *out;  // next 64-bit word (little-endian: two consecutive uint32 stream words)
+  uint64_t acc = 0;
+  unsigned nb = 0;  // bits held in acc, < 64
+  // append the low n bits of v (1 <= n <= 64; v is zero above them)
+  inline void put(uint64_t v, unsigned n) {
+    acc |= v << nb;
+    if (nb + n >= 64) {
+      memcpy(out, &acc, 8);
+      out += 8;
+      acc = nb ? v >> (64 - nb) : 0;
+      nb = nb + n - 64;
+    } else {
+      nb += n;
+    }
+  }
+  inline void flush() {  // the stream's last, partial word (the buffers are padded to 16 bytes)
+    if (nb) memcpy(out, &acc, 8);
+  }
+};
+
+// Body of both SIMD packers (a macro, not a template: the bit deposits and the chunk lambda must
+// be compiled with their function's target options).  Walks the reads of positions [p0, p1) in
+// order; chunk(sp, qp, n, ok, pl, ph) turns n <= CH bases into their masks.
+#define DKB_PACK_ORDERED_LOOP(CH)                                                                        \
+  const uint64_t o0 = offsets[0];                                                                        \
+  size_t lo = 0, hi = n_reads;                                                                           \
+  while (hi - lo > 1) { /* last read whose first position is <= p0 */                                    \
+    const size_t mid = (lo + hi) / 2;                                                                    \
+    if (offsets[mid] - o0 + mid <= p0) lo = mid; else hi = mid;                                          \
+  }                                                                                                      \
+  /* p0 is a multiple of 128: both writers start on a 64-bit word */                                     \
+  BitWriter wb{reinterpret_cast<uint8_t *>(bases2) + p0 / 4}, wm{reinterpret_cast<uint8_t *>(mask1) + p0 / 8}; \
+  for (size_t r = lo; r < n_reads; r++) {                                                                \
+    const uint64_t start = offsets[r] - o0 + r, len = offsets[r + 1] - offsets[r];                       \
+    if (start >= p1) break;                                                                              \
+    uint64_t i = p0 > start ? p0 - start : 0;                 /* first base of the read inside the range */ \
+    const uint64_t end = start + len < p1 ? len : p1 - start; /* one past its last base inside the range */ \
+    const uint8_t *sp = seq + offsets[r];                                                                \
+    const uint8_t *qp = qual ? qual + offsets[r] : nullptr;                                              \
+    while (i < end) {                                                                                    \
+      const unsigned n = end - i < (uint64_t)(CH) ? (unsigned)(end - i) : (unsigned)(CH);                \
+      uint64_t ok, pl, ph;                                                                               \
+      chunk(sp + i, qp ? qp + i : nullptr, n, ok, pl, ph);                                               \
+      const unsigned n0 = n < 32 ? n : 32;                                                               \
+      wb.put(_pdep_u64(pl & 0xFFFFFFFFull, 0x5555555555555555ull) |                                      \
+                 _pdep_u64(ph & 0xFFFFFFFFull, 0xAAAAAAAAAAAAAAAAull), 2 * n0);                          \
+      if ((CH) > 32 && n > 32)                                                                           \
+        wb.put(_pdep_u64(pl >> 32, 0x5555555555555555ull) | _pdep_u64(ph >> 32, 0xAAAAAAAAAAAAAAAAull),  \
+               2 * (n - 32));                                                                            \
+      wm.put(ok, n);                                                                                     \
+      i += n;                                                                                            \
+    }                                                                                                    \
+    if (start + len >= p0 && start + len < p1) { /* the separator after the read: flag 0, code 0 */      \
+      wb.put(0, 2);                                                                                      \
+      wm.put(0, 1);                                                                                      \
+    }                                                                                                    \
+  }                                                                                                      \
+  wb.flush();                                                                                            \
+  wm.flush();
+}  // namespace
+}  // extern "C++"
+
 __attribute__((target("avx2,bmi2"))) static void pack_range_avx2(
     const uint8_t *seq, const uint8_t *qual, const uint64_t *offsets, size_t n_reads, int min_baseq,
     uint32_t *bases2, uint32_t *mask1, uint64_t p0, uint64_t p1) {
-  const uint64_t o0 = offsets[0];
-  size_t lo = 0, hi = n_reads;
-  while (hi - lo > 1) {
-    const size_t mid = (lo + hi) / 2;
-    if (offsets[mid] - o0 + mid <= p0) lo = mid; else hi = mid;
-  }
-  uint8_t *bb = reinterpret_cast<uint8_t *>(bases2), *mb = reinterpret_cast<uint8_t *>(mask1);
   const __m256i lower = _mm256_set1_epi8(0x20), cA = _mm256_set1_epi8('a'), cC = _mm256_set1_epi8('c'),
-                cG = _mm256_set1_epi8('g'), cT = _mm256_set1_epi8('t'), one = _mm256_set1_epi8(1),
-                two = _mm256_set1_epi8(2), three = _mm256_set1_epi8(3);
+                cG = _mm256_set1_epi8('g'), cT = _mm256_set1_epi8('t');
   const int mq = min_baseq < 0 ? 0 : min_baseq > 255 ? 255 : min_baseq;
   const __m256i thr = _mm256_set1_epi8((char)mq);
   const bool never = qual && min_baseq > 255;  // no quality byte can reach the threshold
-  for (size_t r = lo; r < n_reads; r++) {
-    const uint64_t start = offsets[r] - o0 + r, len = offsets[r + 1] - offsets[r];
-    if (start >= p1) break;
-    uint64_t i = p0 > start ? p0 - start : 0;                    // first base of the read inside the range
-    const uint64_t end = start + len < p1 ? len : p1 - start;    // one past its last base inside the range
-    const uint8_t *sp = seq + offsets[r];
-    const uint8_t *qp = qual ? qual + offsets[r] : nullptr;
-    // whole chunks of 32 bases, as long as their 64-bit ORs stay inside this range's words
-    while (i + 32 <= end && start + i + 32 + 64 <= p1 && !never) {
-      __m256i s = _mm256_or_si256(_mm256_loadu_si256(reinterpret_cast<const __m256i *>(sp + i)), lower);
-      const __m256i isA = _mm256_cmpeq_epi8(s, cA), isC = _mm256_cmpeq_epi8(s, cC),
-                    isG = _mm256_cmpeq_epi8(s, cG), isT = _mm256_cmpeq_epi8(s, cT);
-      __m256i ok = _mm256_or_si256(_mm256_or_si256(isA, isC), _mm256_or_si256(isG, isT));
-      if (qp) {
-        const __m256i q = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(qp + i));
-        ok = _mm256_and_si256(ok, _mm256_cmpeq_epi8(_mm256_max_epu8(q, thr), q));  // q >= threshold, unsigned
-      }
-      __m256i code = _mm256_or_si256(_mm256_or_si256(_mm256_and_si256(isC, one), _mm256_and_si256(isG, two)),
-                                     _mm256_and_si256(isT, three));
-      code = _mm256_and_si256(code, ok);
-      const uint32_t m = (uint32_t)_mm256_movemask_epi8(ok);
-      alignas(32) uint64_t lanes[4];
-      _mm256_store_si256(reinterpret_cast<__m256i *>(lanes), code);
-      const uint64_t K = 0x0303030303030303ull;
-      const uint64_t b = _pext_u64(lanes[0], K) | _pext_u64(lanes[1], K) << 16 | _pext_u64(lanes[2], K) << 32 |
-                         _pext_u64(lanes[3], K) << 48;
-      const uint64_t p = start + i;
-      // bases: 64 bits at bit 2p; flags: 32 bits at bit p (byte-granular unaligned ORs)
-      {
-        const uint64_t bit = 2 * p;
-        uint8_t *d = bb + (bit >> 3);
-        const unsigned sh = (unsigned)(bit & 7);  // 0, 2, 4 or 6
-        uint64_t w0, w1 = 0;
-        memcpy(&w0, d, 8);
-        w0 |= b << sh;
-        memcpy(d, &w0, 8);
-        if (sh) {
-          memcpy(&w1, d + 8, 1);
-          w1 |= b >> (64 - sh);
-          memcpy(d + 8, &w1, 1);
+  auto chunk = [&](const uint8_t *sp, const uint8_t *qp, unsigned n, uint64_t &ok, uint64_t &pl, uint64_t &ph)
+                   __attribute__((target("avx2,bmi2"))) {
+        alignas(32) uint8_t ts[32], tq[32];
+        if (n < 32) {  // a read's last bases: through a zero-padded copy (a zero byte is no base)
+          memset(ts, 0, 32);
+          memcpy(ts, sp, n);
+          sp = ts;
+          if (qp) {
+            memset(tq, 0, 32);
+            memcpy(tq, qp, n);
+            qp = tq;
+          }
         }
-      }
-      {
-        uint8_t *d = mb + (p >> 3);
-        const unsigned sh = (unsigned)(p & 7);
-        uint64_t w;
-        memcpy(&w, d, 8);
-        w |= (uint64_t)m << sh;
-        memcpy(d, &w, 8);
-      }
-      i += 32;
-    }
-    for (; i < end; i++) {  // what is left of the read in this range, one base at a time
-      const uint32_t c = LUT.t[sp[i]];
-      const uint32_t ok = (c <= 3) & (!qp || (int)qp[i] >= min_baseq);
-      const uint64_t p = start + i;
-      bases2[p >> 4] |= (ok ? c : 0u) << (2 * (p & 15));
-      mask1[p >> 5] |= ok << (p & 31);
-    }
-    // (the separator after the read keeps its zero flag)
-  }
+        const __m256i s = _mm256_or_si256(_mm256_loadu_si256(reinterpret_cast<const __m256i *>(sp)), lower);
+        const __m256i isA = _mm256_cmpeq_epi8(s, cA), isC = _mm256_cmpeq_epi8(s, cC),
+                      isG = _mm256_cmpeq_epi8(s, cG), isT = _mm256_cmpeq_epi8(s, cT);
+        __m256i okv = _mm256_or_si256(_mm256_or_si256(isA, isC), _mm256_or_si256(isG, isT));
+        if (qp) {
+          const __m256i q = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(qp));
+          okv = _mm256_and_si256(okv, _mm256_cmpeq_epi8(_mm256_max_epu8(q, thr), q));  // q >= threshold, unsigned
+        }
+        const uint32_t m = never ? 0u : (uint32_t)_mm256_movemask_epi8(okv);
+        ok = m;
+        pl = (uint32_t)_mm256_movemask_epi8(_mm256_or_si256(isC, isT)) & m;
+        ph = (uint32_t)_mm256_movemask_epi8(_mm256_or_si256(isG, isT)) & m;
+      };
+  DKB_PACK_ORDERED_LOOP(32)
+}
+
+__attribute__((target("avx512f,avx512bw,bmi2"))) static void pack_range_avx512(
+    const uint8_t *seq, const uint8_t *qual, const uint64_t *offsets, size_t n_reads, int min_baseq,
+    uint32_t *bases2, uint32_t *mask1, uint64_t p0, uint64_t p1) {
+  const __m512i lower = _mm512_set1_epi8(0x20), cA = _mm512_set1_epi8('a'), cC = _mm512_set1_epi8('c'),
+                cG = _mm512_set1_epi8('g'), cT = _mm512_set1_epi8('t');
+  const int mq = min_baseq < 0 ? 0 : min_baseq > 255 ? 255 : min_baseq;
+  const __m512i thr = _mm512_set1_epi8((char)mq);
+  const bool never = qual && min_baseq > 255;
+  auto chunk = [&](const uint8_t *sp, const uint8_t *qp, unsigned n, uint64_t &ok, uint64_t &pl, uint64_t &ph)
+                   __attribute__((target("avx512f,avx512bw,bmi2"))) {
+        // a read's last bases are loaded under a byte mask (masked-out bytes are not touched)
+        const __mmask64 km = n == 64 ? ~0ull : (1ull << n) - 1;
+        const __m512i s = _mm512_or_si512(_mm512_maskz_loadu_epi8(km, sp), lower);
+        const __mmask64 isA = _mm512_cmpeq_epi8_mask(s, cA), isC = _mm512_cmpeq_epi8_mask(s, cC),
+                        isG = _mm512_cmpeq_epi8_mask(s, cG), isT = _mm512_cmpeq_epi8_mask(s, cT);
+        uint64_t m = (uint64_t)(isA | isC | isG | isT);
+        if (qp) m &= (uint64_t)_mm512_cmpge_epu8_mask(_mm512_maskz_loadu_epi8(km, qp), thr);
+        if (never) m = 0;
+        ok = m;
+        pl = (uint64_t)(isC | isT) & m;
+        ph = (uint64_t)(isG | isT) & m;
+      };
+  DKB_PACK_ORDERED_LOOP(64)
 }
 #endif
 
@@ -231,9 +283,14 @@ int dkb_pack_reads(const uint8_t *seq, const uint8_t *qual, const uint64_t *offs
     if (offsets[r + 1] < offsets[r]) return DKB_EINVAL;
   const uint64_t n_pos = dkb_stream_positions(offsets, n_reads);
   const size_t bw = dkb_stream_bases_words(n_pos), mw = dkb_stream_mask_words(n_pos);
-  bool simd = false;
+  // 0 scalar, 1 AVX2 + BMI2 (32 bases per step), 2 AVX-512 BW + BMI2 (64 per step); the best the
+  // CPU has, DKB_PACK_SCALAR=1 / DKB_PACK_ISA=0|1|2 lower it (tests, timing)
+  int simd = 0;
 #ifdef DKB_HAVE_SIMD_PACK
-  simd = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2") && !getenv("DKB_PACK_SCALAR");
+  if (__builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2")) simd = 1;
+  if (simd && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw")) simd = 2;
+  if (getenv("DKB_PACK_SCALAR")) simd = 0;
+  if (const char *e = getenv("DKB_PACK_ISA")) simd = atoi(e) < simd ? (atoi(e) < 0 ? 0 : atoi(e)) : simd;
 #endif
   (void)simd;
   // output words are split between threads on 128-position boundaries: no sharing
@@ -241,6 +298,7 @@ int dkb_pack_reads(const uint8_t *seq, const uint8_t *qual, const uint64_t *offs
   if (n_thr > 32) n_thr = 32;
   if (const char *e = getenv("DKB_PACK_THREADS")) n_thr = atoi(e) > 0 ? (unsigned)atoi(e) : n_thr;
   if (n_thr < 1 || n_pos < (1u << 20)) n_thr = 1;
+  if (n_thr > (n_pos >> 20)) n_thr = (unsigned)(n_pos >> 20) ? (unsigned)(n_pos >> 20) : 1;  // >= 1 M positions per thread
   const uint64_t per = ((n_pos + n_thr - 1) / n_thr + 127) / 128 * 128;
   auto work = [&](unsigned t) {
     const uint64_t p0 = (uint64_t)t * per, p1 = p0 + per < n_pos ? p0 + per : n_pos;
@@ -251,7 +309,8 @@ int dkb_pack_reads(const uint8_t *seq, const uint8_t *qual, const uint64_t *offs
     if (m0 < mw) memset(mask1 + m0, 0, ((m1 < mw ? m1 : mw) - m0) * 4);
     if (p0 < p1 && n_reads) {
 #ifdef DKB_HAVE_SIMD_PACK
-      if (simd) return pack_range_avx2(seq, qual, offsets, n_reads, min_baseq, bases2, mask1, p0, p1);
+      if (simd == 2) return pack_range_avx512(seq, qual, offsets, n_reads, min_baseq, bases2, mask1, p0, p1);
+      if (simd == 1) return pack_range_avx2(seq, qual, offsets, n_reads, min_baseq, bases2, mask1, p0, p1);
 #endif
       pack_range(seq, qual, offsets, n_reads, min_baseq, bases2, mask1, p0, p1);
     }

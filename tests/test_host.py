@@ -167,6 +167,39 @@ def test_pack_reads_threaded_large(dkb, ragged):
     assert st.mask1[(st.n_positions + 31) // 32:].sum() == 0
 
 
+@pytest.mark.parametrize("read_len,ragged", [(1, False), (33, False), (64, False), (65, False), (150, True), (251, False)])
+def test_pack_reads_isa_paths_agree(dkb, read_len, ragged, monkeypatch):
+    """The packer picks the widest path the CPU has (scalar, AVX2 + BMI2: 32 bases per step,
+    AVX-512 BW + BMI2: 64 per step); DKB_PACK_ISA lowers it.  All paths must write the same words -
+    lower case, non-ACGT bytes, every quality byte value, empty reads, a slice whose offsets do not
+    start at 0, thresholds at and beyond the byte range, one thread and several."""
+    from denovo_kmer_b200 import synth
+    g = synth.make_genome(200_000, 9)
+    seq, qual, off = synth.sample_reads([g], (2_500_000 if ragged else 1_200_000) // (read_len + 1) + 100, read_len, 3, ragged=ragged,
+                                        n_rate=0.01, lowq_frac=0.1)
+    rng = np.random.default_rng(read_len)
+    seq, qual = seq.copy(), qual.copy()
+    seq[rng.integers(0, len(seq), len(seq) // 50)] |= 0x20
+    idx = rng.integers(0, len(seq), len(seq) // 300)
+    seq[idx] = rng.integers(0, 256, len(idx)).astype(np.uint8)
+    idx = rng.integers(0, len(qual), len(qual) // 100)
+    qual[idx] = rng.integers(0, 256, len(idx)).astype(np.uint8)
+    off = np.sort(np.concatenate([off, off[rng.integers(0, len(off), len(off) // 20)]]))  # empty reads
+    for offs in (off, off[7:-5]):
+        for threads in ("1", "3"):
+            monkeypatch.setenv("DKB_PACK_THREADS", threads)
+            for mq, use_q in ((20, True), (0, True), (255, True), (256, True), (-3, True), (20, False)):
+                outs = []
+                for isa in ("0", "1", "2"):
+                    monkeypatch.setenv("DKB_PACK_ISA", isa)
+                    st = dkb.pack_reads(seq, qual if use_q else None, offs, mq)
+                    outs.append((st.bases2.copy(), st.mask1.copy(), st.n_positions))
+                for o in outs[1:]:
+                    assert o[2] == outs[0][2] and np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1]), \
+                        (read_len, threads, mq, use_q)
+    assert outs[0][2] > (1 << 20)  # large enough for the threaded split
+
+
 def test_header_is_plain_c_and_links(dkb, tmp_path):
     """include/dkb.h must compile as C11 and a C program must link against libdkb.so and
     call the host-side entry points (the boundary is a C ABI, not a C++ one)."""
