@@ -558,8 +558,19 @@ def run_ours(a):
                 dkb.pack_reads(seq, qual, off, 20)
             return 3 * nb / (time.perf_counter() - t0)
 
+        def zero_list_rate(threads):  # dense flags -> zero list (what dkb_batch_submit_sparse sends)
+            os.environ["DKB_PACK_THREADS"] = str(threads)
+            seq, qual, off = raw[0]
+            st = dkb.pack_reads(seq, qual, off, 20)
+            dkb.mask_to_zero_list(st.mask1, st.n_positions)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                dkb.mask_to_zero_list(st.mask1, st.n_positions)
+            return 3 * nb / (time.perf_counter() - t0)
+
         cores = min(os.cpu_count() or 1, 32)
         r1, rn = pack_rate(1), pack_rate(cores)
+        z1, zn = zero_list_rate(1), zero_list_rate(cores)
         os.environ.pop("DKB_PACK_THREADS", None)
 
         pinned = []  # the BAM layer's decoded records, in page-locked buffers next to the GPU
@@ -581,6 +592,7 @@ def run_ours(a):
             reads_step()
         el = time.perf_counter() - t0
         feeders = {"host_packer_bases_per_s": {"1_thread": r1, f"{cores}_threads": rn},
+                   "zero_list_bases_per_s": {"1_thread": z1, f"{cores}_threads": zn},
                    "device_packer_e2e": {"value": 5 * 3 * nb / el, "unit": UNIT,
                                          "h2d_bytes_per_base": 2.0 + 8.0 / READ_LEN,
                                          "what": "dkb_batch_submit_reads: pinned ASCII reads + quality bytes -> H2D -> "

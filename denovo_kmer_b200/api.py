@@ -96,8 +96,8 @@ def mask_to_zero_list(mask1, n_positions: int):
     nb = int(L.dkb_zero_list_blocks(n_positions))
     zoff = np.zeros(nb + 1, dtype=np.uint32)
     used = C.c_size_t(0)
-    check(L.dkb_mask_to_zero_list(_p(mask1, u32p), n_positions, _p(zoff, u32p), None, 0, C.byref(used)))
-    zbytes = np.zeros(max(int(used.value), 1), dtype=np.uint8)
+    # one call: a zero list is never longer than the dense flags (256 bytes per 2048-position block)
+    zbytes = np.empty(max(nb * 256, 1), dtype=np.uint8)
     check(L.dkb_mask_to_zero_list(_p(mask1, u32p), n_positions, _p(zoff, u32p), _p(zbytes, u8p),
                                   len(zbytes), C.byref(used)))
     return zoff, zbytes[: int(used.value)]

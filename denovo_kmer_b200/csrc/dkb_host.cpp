@@ -331,19 +331,22 @@ namespace {
 constexpr uint64_t ZL_BLOCK = 2048;
 constexpr uint32_t ZL_RAW_BIT = 0x80000000u;
 
-inline bool flag_at(const uint32_t *mask1, uint64_t p) { return (mask1[p >> 5] >> (p & 31)) & 1u; }
 
-// Bytes the gap coding of block [p0, p1) needs (p0 a multiple of 32); positions >= n_pos of the
-// last block are not coded.  Word at a time: the zeros of a word are found with ctz.
+// Gap coding of block [p0, p1) (p0 a multiple of 2048) into out (nullptr: only count); returns
+// its length in bytes.  Positions >= p1 - the end of the stream - are not coded.  64 flags at a
+// time (the stream's mask words come in groups of four, so the last 64-bit load is in bounds);
+// the zeros of a word are found with ctz.  out must have room for 2048 + 16 bytes.
 size_t zl_block_bytes(const uint32_t *mask1, uint64_t p0, uint64_t p1, uint8_t *out) {
   size_t n = 0;
   uint64_t gap = 0;
-  for (uint64_t wp = p0; wp < p1; wp += 32) {
-    const uint32_t valid = p1 - wp >= 32 ? 0xFFFFFFFFu : (1u << (p1 - wp)) - 1u;  // positions of this word in range
-    uint32_t zeros = ~mask1[wp >> 5] & valid;
-    uint32_t done = 0;  // positions of the word already accounted for
+  for (uint64_t wp = p0; wp < p1; wp += 64) {
+    const unsigned nvalid = p1 - wp >= 64 ? 64u : (unsigned)(p1 - wp);  // positions of this word in range
+    uint64_t w;
+    memcpy(&w, mask1 + (wp >> 5), 8);
+    uint64_t zeros = ~w & (nvalid == 64 ? ~0ull : (1ull << nvalid) - 1);
+    unsigned done = 0;  // positions of the word already accounted for
     while (zeros) {
-      const uint32_t t = (uint32_t)__builtin_ctz(zeros);
+      const unsigned t = (unsigned)__builtin_ctzll(zeros);
       zeros &= zeros - 1;
       gap += t - done;
       done = t + 1;
@@ -356,7 +359,7 @@ size_t zl_block_bytes(const uint32_t *mask1, uint64_t p0, uint64_t p1, uint8_t *
       n++;
       gap = 0;
     }
-    gap += (uint32_t)__builtin_popcount(valid) - done;
+    gap += nvalid - done;
   }
   return n;
 }
@@ -369,34 +372,57 @@ int dkb_mask_to_zero_list(const uint32_t *mask1, uint64_t n_positions, uint32_t 
   if (!zbytes_used || (n_positions && (!mask1 || !zoff))) return DKB_EINVAL;
   const size_t nb = dkb_zero_list_blocks(n_positions);
   if (nb >= 0x7FFFFFFFu / 256) return DKB_EINVAL;
-  // pass 1: size of every block (gap coding, or the plain 256 bytes when that is shorter)
+  // ONE pass over the flags: every thread codes a contiguous run of blocks into its own scratch
+  // (gap coding, or the block's plain 256 bytes when that is shorter) and notes the lengths; the
+  // offsets are their prefix sum, and each thread's scratch is then copied to its place in one piece.
   std::vector<uint32_t> len(nb);
   unsigned n_thr = std::thread::hardware_concurrency();
   if (n_thr > 32) n_thr = 32;
   if (const char *e = getenv("DKB_PACK_THREADS")) n_thr = atoi(e) > 0 ? (unsigned)atoi(e) : n_thr;
-  if (n_thr < 1 || nb < 64) n_thr = 1;
-  auto parallel = [&](auto &&fn) {
-    if (n_thr == 1) return fn(0, nb);
-    std::vector<std::thread> pool;
-    const size_t per = (nb + n_thr - 1) / n_thr;
-    for (unsigned t = 0; t < n_thr; t++) {
-      const size_t a = (size_t)t * per, b = a + per < nb ? a + per : nb;
-      if (a < b) pool.emplace_back(fn, a, b);
+  if (n_thr > nb / 512) n_thr = (unsigned)(nb / 512);  // >= 1 M positions per thread
+  if (n_thr < 1) n_thr = 1;
+  const size_t per = (nb + n_thr - 1) / n_thr;
+  const bool fill = zbytes != nullptr;
+  std::vector<std::vector<uint8_t>> scratch(n_thr);
+  auto code = [&](unsigned t) {
+    const size_t a = (size_t)t * per, b = a + per < nb ? a + per : nb;
+    std::vector<uint8_t> &buf = scratch[t];
+    size_t used = 0;
+    uint8_t tmp[2048 + 16];
+    if (fill && a < b) buf.resize((b - a) * 96 + 4096);
+    for (size_t i = a; i < b; i++) {
+      const uint64_t p0 = (uint64_t)i * ZL_BLOCK, p1 = p0 + ZL_BLOCK < n_positions ? p0 + ZL_BLOCK : n_positions;
+      if (!fill) {
+        const size_t g = zl_block_bytes(mask1, p0, p1, nullptr);
+        len[i] = g > 256 ? (256u | ZL_RAW_BIT) : (uint32_t)g;
+        continue;
+      }
+      if (buf.size() < used + 2048 + 16) buf.resize(buf.size() * 2);
+      const size_t g = zl_block_bytes(mask1, p0, p1, tmp);
+      uint8_t *dst = buf.data() + used;
+      if (g > 256) {  // the block's 64 mask words, little-endian; flags past the stream are 0
+        for (uint32_t wi = 0; wi < 64; wi++) {
+          const uint64_t m = p0 / 32 + wi;
+          uint32_t v = m * 32 < n_positions ? mask1[m] : 0u;
+          if (m * 32 + 32 > n_positions && m * 32 < n_positions) v &= (1u << (n_positions - m * 32)) - 1u;
+          for (int k = 0; k < 4; k++) dst[4 * wi + k] = (uint8_t)(v >> (8 * k));
+        }
+        len[i] = 256u | ZL_RAW_BIT;
+        used += 256;
+      } else {
+        memcpy(dst, tmp, g);
+        len[i] = (uint32_t)g;
+        used += g;
+      }
     }
+  };
+  auto parallel = [&](auto &&fn) {
+    if (n_thr == 1) return fn(0u);
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < n_thr; t++) pool.emplace_back(fn, t);
     for (auto &th : pool) th.join();
   };
-  auto span = [&](size_t b, uint64_t &p0, uint64_t &p1) {
-    p0 = (uint64_t)b * ZL_BLOCK;
-    p1 = p0 + ZL_BLOCK < n_positions ? p0 + ZL_BLOCK : n_positions;
-  };
-  parallel([&](size_t a, size_t b) {
-    for (size_t i = a; i < b; i++) {
-      uint64_t p0, p1;
-      span(i, p0, p1);
-      const size_t g = zl_block_bytes(mask1, p0, p1, nullptr);
-      len[i] = g > 256 ? (256u | ZL_RAW_BIT) : (uint32_t)g;
-    }
-  });
+  parallel(code);
   size_t total = 0;
   for (size_t i = 0; i < nb; i++) {
     zoff[i] = (uint32_t)total | (len[i] & ZL_RAW_BIT);
@@ -404,24 +430,13 @@ int dkb_mask_to_zero_list(const uint32_t *mask1, uint64_t n_positions, uint32_t 
   }
   if (n_positions) zoff[nb] = (uint32_t)total;
   *zbytes_used = total;
-  if (!zbytes) return DKB_OK;  // sizing call
+  if (!fill) return DKB_OK;  // sizing call
   if (total > zbytes_cap) return DKB_EINVAL;
-  parallel([&](size_t a, size_t b) {
-    for (size_t i = a; i < b; i++) {
-      uint64_t p0, p1;
-      span(i, p0, p1);
-      uint8_t *dst = zbytes + (zoff[i] & ~ZL_RAW_BIT);
-      if (zoff[i] & ZL_RAW_BIT) {  // the block's 64 mask words, little-endian; words past the stream are 0
-        for (uint32_t wi = 0; wi < 64; wi++) {
-          const uint64_t m = p0 / 32 + wi;
-          uint32_t v = m * 32 < n_positions ? mask1[m] : 0u;
-          if (m * 32 + 32 > n_positions && m * 32 < n_positions) v &= (1u << (n_positions - m * 32)) - 1u;
-          for (int k = 0; k < 4; k++) dst[4 * wi + k] = (uint8_t)(v >> (8 * k));
-        }
-      } else {
-        zl_block_bytes(mask1, p0, p1, dst);
-      }
-    }
+  parallel([&](unsigned t) {
+    const size_t a = (size_t)t * per, b = a + per < nb ? a + per : nb;
+    if (a >= b) return;
+    const size_t first = zoff[a] & ~ZL_RAW_BIT, last = b < nb ? (zoff[b] & ~ZL_RAW_BIT) : total;
+    memcpy(zbytes + first, scratch[t].data(), last - first);
   });
   return DKB_OK;
 }

@@ -355,6 +355,14 @@ def test_zero_list_round_trip(dkb, orc):
         assert len(zoff) == (n + 2047) // 2048 + 1 and int(zoff[-1]) == len(zbytes)
         back = orc.expand_zero_list(zoff, zbytes, n)
         assert np.array_equal(back, flags), n
+        # the sizing form (zbytes == NULL) reports the same offsets and length
+        import ctypes as C
+        from denovo_kmer_b200 import _lib
+        zoff2 = np.zeros_like(zoff)
+        used = C.c_size_t(0)
+        rc = _lib.lib().dkb_mask_to_zero_list(mask1.ctypes.data_as(C.POINTER(C.c_uint32)), n,
+                                              zoff2.ctypes.data_as(C.POINTER(C.c_uint32)), None, 0, C.byref(used))
+        assert rc == 0 and used.value == len(zbytes) and np.array_equal(zoff2, zoff)
         return len(zbytes)
 
     for n in (1, 31, 2047, 2048, 2049, 5000, 70_001):
