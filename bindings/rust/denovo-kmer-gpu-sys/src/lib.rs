@@ -52,6 +52,9 @@ extern "C" {
     pub fn dkb_pack_reads(seq: *const u8, qual: *const u8, offsets: *const u64, n_reads: usize,
                           min_baseq: c_int, bases2: *mut u32, mask1: *mut u32,
                           n_positions_out: *mut u64) -> c_int;
+    pub fn dkb_pack_reads_fmt(seq: *const u8, seq_format: c_int, qual: *const u8, offsets: *const u64,
+                              n_reads: usize, min_baseq: c_int, bases2: *mut u32, mask1: *mut u32,
+                              n_positions_out: *mut u64) -> c_int;
     pub fn dkb_zero_list_blocks(n_positions: u64) -> usize;
     pub fn dkb_mask_to_zero_list(mask1: *const u32, n_positions: u64, zoff: *mut u32, zbytes: *mut u8,
                                  zbytes_cap: usize, zbytes_used: *mut usize) -> c_int;

@@ -5,7 +5,8 @@ use denovo_kmer_gpu::{comm_unique_id, variant_kmers, Candidate, Counter, Thresho
 
 /// What the reference's BAM layer yields: decoded reads of one sample, in batches.
 pub trait ReadSource {
-    /// Fills `seq`, `qual`, `offsets` (offsets[0] = 0) with the next batch; false at end of file.
+    /// Fills `seq` (ASCII here; `record.seq().encoded` with `four_bit = true` skips the decode),
+    /// `qual`, `offsets` (offsets[0] = 0) with the next batch; false at end of file.
     fn next_batch(&mut self, seq: &mut Vec<u8>, qual: &mut Vec<u8>, offsets: &mut Vec<u64>) -> bool;
 }
 
@@ -27,7 +28,7 @@ pub fn run_trio(device: i32, k: i32, min_baseq: i32, thr: Thresholds, cands: &[C
                 kc.sync()?; // both pinned buffers are in use: wait before repacking one
                 in_flight = 0;
             }
-            let batch = packer.next(&seq, Some(qual.as_slice()), &off)?;
+            let batch = packer.next(&seq, false, Some(qual.as_slice()), &off)?;
             kc.submit(batch, sample as i32)?;
             in_flight += 1;
         }

@@ -291,10 +291,11 @@ impl BatchPacker {
         Ok(BatchPacker { ctx: c.ctx, bufs: [mk()?, mk()?], next: 0, min_baseq })
     }
 
-    /// `dkb_pack_reads` into the next buffer: `seq`/`qual` are the reads back to back, read r at
-    /// `offsets[r]..offsets[r + 1]`.  The buffer returned was last handed out two calls ago:
+    /// `dkb_pack_reads_fmt` into the next buffer: `seq`/`qual` are the reads back to back, read r at
+    /// `offsets[r]..offsets[r + 1]` (in bases).  `four_bit`: `seq` holds BAM 4-bit codes
+    /// (`record.seq().encoded`, every read on a byte boundary) instead of ASCII - no decode pass.  The buffer returned was last handed out two calls ago:
     /// call [`Counter::sync`] at least every second batch before packing again.
-    pub fn next(&mut self, seq: &[u8], qual: Option<&[u8]>, offsets: &[u64]) -> Result<&PinnedBatch> {
+    pub fn next(&mut self, seq: &[u8], four_bit: bool, qual: Option<&[u8]>, offsets: &[u64]) -> Result<&PinnedBatch> {
         let n_reads = offsets.len().saturating_sub(1);
         let n_pos = unsafe { sys::dkb_stream_positions(offsets.as_ptr(), n_reads) };
         let b = &mut self.bufs[self.next];
@@ -305,8 +306,8 @@ impl BatchPacker {
         }
         let mut out = 0u64;
         check(unsafe {
-            sys::dkb_pack_reads(seq.as_ptr(), qual.map_or(ptr::null(), |q| q.as_ptr()), offsets.as_ptr(),
-                                n_reads, self.min_baseq, b.bases2, b.mask1, &mut out)
+            sys::dkb_pack_reads_fmt(seq.as_ptr(), four_bit as c_int, qual.map_or(ptr::null(), |q| q.as_ptr()),
+                                    offsets.as_ptr(), n_reads, self.min_baseq, b.bases2, b.mask1, &mut out)
         }, self.ctx)?;
         b.n_positions = out;
         b.n_bases = if n_reads > 0 { offsets[n_reads] - offsets[0] } else { 0 };

@@ -52,6 +52,7 @@ SYMBOLS = {
     "dkb_stream_bases_words": (C.c_size_t, [C.c_uint64]),
     "dkb_stream_mask_words": (C.c_size_t, [C.c_uint64]),
     "dkb_pack_reads": (C.c_int, [u8p, u8p, u64p, C.c_size_t, C.c_int, u32p, u32p, u64p]),
+    "dkb_pack_reads_fmt": (C.c_int, [u8p, C.c_int, u8p, u64p, C.c_size_t, C.c_int, u32p, u32p, u64p]),
     "dkb_zero_list_blocks": (C.c_size_t, [C.c_uint64]),
     "dkb_mask_to_zero_list": (C.c_int, [u32p, C.c_uint64, u32p, u8p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "dkb_variant_kmers": (C.c_int, [C.POINTER(C.c_char_p)] * 4 + [C.c_size_t, C.c_int, C.c_int,

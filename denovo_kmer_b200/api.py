@@ -63,9 +63,12 @@ def stream_words(n_positions: int):
     return int(L.dkb_stream_bases_words(n_positions)), int(L.dkb_stream_mask_words(n_positions))
 
 
-def pack_reads(seq, qual, offsets, min_baseq: int = DEFAULT_MIN_BASEQ, pinned: bool = False):
+def pack_reads(seq, qual, offsets, min_baseq: int = DEFAULT_MIN_BASEQ, pinned: bool = False,
+               four_bit: bool = False):
     """seq/qual: uint8 arrays of concatenated reads (qual may be None);
-    offsets: uint64[n_reads + 1].  Returns a ReadStream in host memory."""
+    offsets: uint64[n_reads + 1] (in bases).  four_bit: seq holds BAM 4-bit codes, high nibble
+    first, every read on a byte boundary (include/dkb.h, dkb_pack_reads_fmt) instead of ASCII.
+    Returns a ReadStream in host memory."""
     L = _lib.lib()
     seq = np.ascontiguousarray(seq, dtype=np.uint8)
     qual = None if qual is None else np.ascontiguousarray(qual, dtype=np.uint8)
@@ -83,8 +86,8 @@ def pack_reads(seq, qual, offsets, min_baseq: int = DEFAULT_MIN_BASEQ, pinned: b
         bases2 = np.empty(max(bw, 1), dtype=np.uint32)
         mask1 = np.empty(max(mw, 1), dtype=np.uint32)
     out = C.c_uint64(0)
-    check(L.dkb_pack_reads(_p(seq, u8p), _p(qual, u8p), _p(offsets, u64p), n_reads, min_baseq,
-                           _p(bases2, u32p), _p(mask1, u32p), C.byref(out)))
+    check(L.dkb_pack_reads_fmt(_p(seq, u8p), int(four_bit), _p(qual, u8p), _p(offsets, u64p), n_reads,
+                               min_baseq, _p(bases2, u32p), _p(mask1, u32p), C.byref(out)))
     n_bases = int(offsets[-1] - offsets[0]) if n_reads else 0
     return ReadStream(bases2, mask1, int(out.value), n_bases)
 

@@ -28,6 +28,8 @@ struct BaseLut {
   }
 };
 const BaseLut LUT;
+// BAM 4-bit code (=ACMGRSVTWYHKDBN: A=1 C=2 G=4 T=8) -> 2-bit code; 4 = not a plain base
+const uint8_t NIB_LUT[16] = {4, 0, 1, 4, 2, 4, 4, 4, 3, 4, 4, 4, 4, 4, 4, 4};
 
 inline uint64_t kmask(int k) { return (1ull << (2 * k)) - 1; }
 
@@ -75,7 +77,8 @@ size_t dkb_stream_mask_words(uint64_t n_positions) { return (size_t)((n_position
 
 // Pack stream positions [p0, p1) (p0 a multiple of 32, so no output word is shared
 // between two calls).  Position of read r's first base: offsets[r] - offsets[0] + r.
-static void pack_range(const uint8_t *seq, const uint8_t *qual, const uint64_t *offsets,
+// nib (4-bit input only, else nullptr): byte offset of every read's first pair of codes.
+static void pack_range(const uint8_t *seq, const uint64_t *nib, const uint8_t *qual, const uint64_t *offsets,
                        size_t n_reads, int min_baseq, uint32_t *bases2, uint32_t *mask1,
                        uint64_t p0, uint64_t p1) {
   const uint64_t o0 = offsets[0];
@@ -106,11 +109,11 @@ static void pack_range(const uint8_t *seq, const uint8_t *qual, const uint64_t *
     uint64_t i = p > start ? p - start : 0;       // first base of this read inside the range
     if (start + i > p) advance(start + i < p1 ? start + i : p1);
     if (p >= p1) break;
-    const uint8_t *sp = seq + offsets[r];
+    const uint8_t *sp = nib ? seq + nib[r] : seq + offsets[r];
     const uint8_t *qp = qual ? qual + offsets[r] : nullptr;
     const uint64_t end = start + len < p1 ? len : p1 - start;  // bases of this read in range
     for (; i < end; i++) {
-      const uint32_t c = LUT.t[sp[i]];
+      const uint32_t c = nib ? NIB_LUT[(i & 1) ? (sp[i >> 1] & 15u) : (sp[i >> 1] >> 4)] : LUT.t[sp[i]];
       const uint32_t ok = (c <= 3) & (!qp || (int)qp[i] >= min_baseq);
       const uint32_t sh = (uint32_t)(p & 15);
       cur_b |= (ok ? c : 0u) << (2 * sh);
@@ -185,12 +188,19 @@ struct BitWriter {
     if (start >= p1) break;                                                                              \
     uint64_t i = p0 > start ? p0 - start : 0;                 /* first base of the read inside the range */ \
     const uint64_t end = start + len < p1 ? len : p1 - start; /* one past its last base inside the range */ \
-    const uint8_t *sp = seq + offsets[r];                                                                \
+    const uint8_t *sp = nib ? seq + nib[r] : seq + offsets[r];                                           \
     const uint8_t *qp = qual ? qual + offsets[r] : nullptr;                                              \
+    if (nib && (i & 1) && i < end) { /* 4-bit input cut inside a byte: its low code on its own */        \
+      const uint32_t c = NIB_LUT[sp[i >> 1] & 15u];                                                      \
+      const uint32_t okb = (c <= 3) & (!qp || (int)qp[i] >= min_baseq);                                  \
+      wb.put(okb ? c : 0u, 2);                                                                           \
+      wm.put(okb, 1);                                                                                    \
+      i++;                                                                                               \
+    }                                                                                                    \
     while (i < end) {                                                                                    \
       const unsigned n = end - i < (uint64_t)(CH) ? (unsigned)(end - i) : (unsigned)(CH);                \
       uint64_t ok, pl, ph;                                                                               \
-      chunk(sp + i, qp ? qp + i : nullptr, n, ok, pl, ph);                                               \
+      chunk(nib ? sp + (i >> 1) : sp + i, qp ? qp + i : nullptr, n, ok, pl, ph);                         \
       const unsigned n0 = n < 32 ? n : 32;                                                               \
       wb.put(_pdep_u64(pl & 0xFFFFFFFFull, 0x5555555555555555ull) |                                      \
                  _pdep_u64(ph & 0xFFFFFFFFull, 0xAAAAAAAAAAAAAAAAull), 2 * n0);                          \
@@ -211,8 +221,8 @@ struct BitWriter {
 }  // extern "C++"
 
 __attribute__((target("avx2,bmi2"))) static void pack_range_avx2(
-    const uint8_t *seq, const uint8_t *qual, const uint64_t *offsets, size_t n_reads, int min_baseq,
-    uint32_t *bases2, uint32_t *mask1, uint64_t p0, uint64_t p1) {
+    const uint8_t *seq, const uint64_t *nib, const uint8_t *qual, const uint64_t *offsets, size_t n_reads,
+    int min_baseq, uint32_t *bases2, uint32_t *mask1, uint64_t p0, uint64_t p1) {
   const __m256i lower = _mm256_set1_epi8(0x20), cA = _mm256_set1_epi8('a'), cC = _mm256_set1_epi8('c'),
                 cG = _mm256_set1_epi8('g'), cT = _mm256_set1_epi8('t');
   const int mq = min_baseq < 0 ? 0 : min_baseq > 255 ? 255 : min_baseq;
@@ -221,9 +231,10 @@ __attribute__((target("avx2,bmi2"))) static void pack_range_avx2(
   auto chunk = [&](const uint8_t *sp, const uint8_t *qp, unsigned n, uint64_t &ok, uint64_t &pl, uint64_t &ph)
                    __attribute__((target("avx2,bmi2"))) {
         alignas(32) uint8_t ts[32], tq[32];
-        if (n < 32) {  // a read's last bases: through a zero-padded copy (a zero byte is no base)
+        const unsigned sbytes = nib ? (n + 1) / 2 : n;  // input bytes of this chunk
+        if (n < 32) {  // a read's last bases: through a zero-padded copy (a zero byte / code is no base)
           memset(ts, 0, 32);
-          memcpy(ts, sp, n);
+          memcpy(ts, sp, sbytes);
           sp = ts;
           if (qp) {
             memset(tq, 0, 32);
@@ -231,15 +242,31 @@ __attribute__((target("avx2,bmi2"))) static void pack_range_avx2(
             qp = tq;
           }
         }
-        const __m256i s = _mm256_or_si256(_mm256_loadu_si256(reinterpret_cast<const __m256i *>(sp)), lower);
-        const __m256i isA = _mm256_cmpeq_epi8(s, cA), isC = _mm256_cmpeq_epi8(s, cC),
-                      isG = _mm256_cmpeq_epi8(s, cG), isT = _mm256_cmpeq_epi8(s, cT);
+        __m256i isA, isC, isG, isT;
+        if (nib) {
+          // 16 bytes = 32 codes, high nibble first: widen every byte to 16 bits and put its high
+          // nibble in the low byte, its low nibble in the high byte - bytes in base order
+          const __m256i w = _mm256_cvtepu8_epi16(_mm_loadu_si128(reinterpret_cast<const __m128i *>(sp)));
+          const __m256i c4 = _mm256_or_si256(_mm256_and_si256(_mm256_srli_epi16(w, 4), _mm256_set1_epi16(0x000F)),
+                                             _mm256_slli_epi16(_mm256_and_si256(w, _mm256_set1_epi16(0x000F)), 8));
+          isA = _mm256_cmpeq_epi8(c4, _mm256_set1_epi8(1));
+          isC = _mm256_cmpeq_epi8(c4, _mm256_set1_epi8(2));
+          isG = _mm256_cmpeq_epi8(c4, _mm256_set1_epi8(4));
+          isT = _mm256_cmpeq_epi8(c4, _mm256_set1_epi8(8));
+        } else {
+          const __m256i s = _mm256_or_si256(_mm256_loadu_si256(reinterpret_cast<const __m256i *>(sp)), lower);
+          isA = _mm256_cmpeq_epi8(s, cA);
+          isC = _mm256_cmpeq_epi8(s, cC);
+          isG = _mm256_cmpeq_epi8(s, cG);
+          isT = _mm256_cmpeq_epi8(s, cT);
+        }
         __m256i okv = _mm256_or_si256(_mm256_or_si256(isA, isC), _mm256_or_si256(isG, isT));
         if (qp) {
           const __m256i q = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(qp));
           okv = _mm256_and_si256(okv, _mm256_cmpeq_epi8(_mm256_max_epu8(q, thr), q));  // q >= threshold, unsigned
         }
-        const uint32_t m = never ? 0u : (uint32_t)_mm256_movemask_epi8(okv);
+        // (an odd chunk's last byte carries a padding code: nothing beyond base n counts)
+        const uint32_t m = never ? 0u : (uint32_t)_mm256_movemask_epi8(okv) & (n == 32 ? ~0u : (1u << n) - 1u);
         ok = m;
         pl = (uint32_t)_mm256_movemask_epi8(_mm256_or_si256(isC, isT)) & m;
         ph = (uint32_t)_mm256_movemask_epi8(_mm256_or_si256(isG, isT)) & m;
@@ -247,22 +274,39 @@ __attribute__((target("avx2,bmi2"))) static void pack_range_avx2(
   DKB_PACK_ORDERED_LOOP(32)
 }
 
-__attribute__((target("avx512f,avx512bw,bmi2"))) static void pack_range_avx512(
-    const uint8_t *seq, const uint8_t *qual, const uint64_t *offsets, size_t n_reads, int min_baseq,
-    uint32_t *bases2, uint32_t *mask1, uint64_t p0, uint64_t p1) {
+__attribute__((target("avx512f,avx512bw,avx512vl,bmi2"))) static void pack_range_avx512(
+    const uint8_t *seq, const uint64_t *nib, const uint8_t *qual, const uint64_t *offsets, size_t n_reads,
+    int min_baseq, uint32_t *bases2, uint32_t *mask1, uint64_t p0, uint64_t p1) {
   const __m512i lower = _mm512_set1_epi8(0x20), cA = _mm512_set1_epi8('a'), cC = _mm512_set1_epi8('c'),
                 cG = _mm512_set1_epi8('g'), cT = _mm512_set1_epi8('t');
   const int mq = min_baseq < 0 ? 0 : min_baseq > 255 ? 255 : min_baseq;
   const __m512i thr = _mm512_set1_epi8((char)mq);
   const bool never = qual && min_baseq > 255;
   auto chunk = [&](const uint8_t *sp, const uint8_t *qp, unsigned n, uint64_t &ok, uint64_t &pl, uint64_t &ph)
-                   __attribute__((target("avx512f,avx512bw,bmi2"))) {
+                   __attribute__((target("avx512f,avx512bw,avx512vl,bmi2"))) {
         // a read's last bases are loaded under a byte mask (masked-out bytes are not touched)
         const __mmask64 km = n == 64 ? ~0ull : (1ull << n) - 1;
-        const __m512i s = _mm512_or_si512(_mm512_maskz_loadu_epi8(km, sp), lower);
-        const __mmask64 isA = _mm512_cmpeq_epi8_mask(s, cA), isC = _mm512_cmpeq_epi8_mask(s, cC),
-                        isG = _mm512_cmpeq_epi8_mask(s, cG), isT = _mm512_cmpeq_epi8_mask(s, cT);
-        uint64_t m = (uint64_t)(isA | isC | isG | isT);
+        __mmask64 isA, isC, isG, isT;
+        if (nib) {
+          // 32 bytes = 64 codes, high nibble first (see the AVX2 path); bytes beyond the read's
+          // last pair are not touched
+          const unsigned sb = (n + 1) / 2;
+          const __mmask32 kb = sb == 32 ? ~0u : (1u << sb) - 1u;
+          const __m512i w = _mm512_cvtepu8_epi16(_mm256_maskz_loadu_epi8(kb, sp));
+          const __m512i c4 = _mm512_or_si512(_mm512_and_si512(_mm512_srli_epi16(w, 4), _mm512_set1_epi16(0x000F)),
+                                             _mm512_slli_epi16(_mm512_and_si512(w, _mm512_set1_epi16(0x000F)), 8));
+          isA = _mm512_cmpeq_epi8_mask(c4, _mm512_set1_epi8(1));
+          isC = _mm512_cmpeq_epi8_mask(c4, _mm512_set1_epi8(2));
+          isG = _mm512_cmpeq_epi8_mask(c4, _mm512_set1_epi8(4));
+          isT = _mm512_cmpeq_epi8_mask(c4, _mm512_set1_epi8(8));
+        } else {
+          const __m512i s = _mm512_or_si512(_mm512_maskz_loadu_epi8(km, sp), lower);
+          isA = _mm512_cmpeq_epi8_mask(s, cA);
+          isC = _mm512_cmpeq_epi8_mask(s, cC);
+          isG = _mm512_cmpeq_epi8_mask(s, cG);
+          isT = _mm512_cmpeq_epi8_mask(s, cT);
+        }
+        uint64_t m = (uint64_t)(isA | isC | isG | isT) & (uint64_t)km;  // (an odd chunk's padding code)
         if (qp) m &= (uint64_t)_mm512_cmpge_epu8_mask(_mm512_maskz_loadu_epi8(km, qp), thr);
         if (never) m = 0;
         ok = m;
@@ -276,11 +320,29 @@ __attribute__((target("avx512f,avx512bw,bmi2"))) static void pack_range_avx512(
 int dkb_pack_reads(const uint8_t *seq, const uint8_t *qual, const uint64_t *offsets,
                    size_t n_reads, int min_baseq, uint32_t *bases2, uint32_t *mask1,
                    uint64_t *n_positions_out) {
+  return dkb_pack_reads_fmt(seq, 0, qual, offsets, n_reads, min_baseq, bases2, mask1, n_positions_out);
+}
+
+int dkb_pack_reads_fmt(const uint8_t *seq, int seq_format, const uint8_t *qual, const uint64_t *offsets,
+                       size_t n_reads, int min_baseq, uint32_t *bases2, uint32_t *mask1,
+                       uint64_t *n_positions_out) {
   if (!offsets && n_reads) return DKB_EINVAL;
   if (!bases2 || !mask1) return DKB_EINVAL;
   if (n_reads && !seq) return DKB_EINVAL;
+  if (seq_format != 0 && seq_format != 1) return DKB_EINVAL;
   for (size_t r = 0; r < n_reads; r++)
     if (offsets[r + 1] < offsets[r]) return DKB_EINVAL;
+  // BAM keeps every read's 4-bit codes byte-aligned: (len + 1) / 2 bytes per read, back to back
+  std::vector<uint64_t> nib_of;
+  if (seq_format == 1) {
+    nib_of.resize(n_reads);
+    uint64_t b = 0;
+    for (size_t r = 0; r < n_reads; r++) {
+      nib_of[r] = b;
+      b += (offsets[r + 1] - offsets[r] + 1) / 2;
+    }
+  }
+  const uint64_t *nib = seq_format == 1 ? nib_of.data() : nullptr;
   const uint64_t n_pos = dkb_stream_positions(offsets, n_reads);
   const size_t bw = dkb_stream_bases_words(n_pos), mw = dkb_stream_mask_words(n_pos);
   // 0 scalar, 1 AVX2 + BMI2 (32 bases per step), 2 AVX-512 BW + BMI2 (64 per step); the best the
@@ -288,7 +350,9 @@ int dkb_pack_reads(const uint8_t *seq, const uint8_t *qual, const uint64_t *offs
   int simd = 0;
 #ifdef DKB_HAVE_SIMD_PACK
   if (__builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2")) simd = 1;
-  if (simd && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw")) simd = 2;
+  if (simd && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") &&
+      __builtin_cpu_supports("avx512vl"))
+    simd = 2;
   if (getenv("DKB_PACK_SCALAR")) simd = 0;
   if (const char *e = getenv("DKB_PACK_ISA")) simd = atoi(e) < simd ? (atoi(e) < 0 ? 0 : atoi(e)) : simd;
 #endif
@@ -309,10 +373,10 @@ int dkb_pack_reads(const uint8_t *seq, const uint8_t *qual, const uint64_t *offs
     if (m0 < mw) memset(mask1 + m0, 0, ((m1 < mw ? m1 : mw) - m0) * 4);
     if (p0 < p1 && n_reads) {
 #ifdef DKB_HAVE_SIMD_PACK
-      if (simd == 2) return pack_range_avx512(seq, qual, offsets, n_reads, min_baseq, bases2, mask1, p0, p1);
-      if (simd == 1) return pack_range_avx2(seq, qual, offsets, n_reads, min_baseq, bases2, mask1, p0, p1);
+      if (simd == 2) return pack_range_avx512(seq, nib, qual, offsets, n_reads, min_baseq, bases2, mask1, p0, p1);
+      if (simd == 1) return pack_range_avx2(seq, nib, qual, offsets, n_reads, min_baseq, bases2, mask1, p0, p1);
 #endif
-      pack_range(seq, qual, offsets, n_reads, min_baseq, bases2, mask1, p0, p1);
+      pack_range(seq, nib, qual, offsets, n_reads, min_baseq, bases2, mask1, p0, p1);
     }
   };
   if (n_thr == 1) {

@@ -118,6 +118,14 @@ size_t dkb_stream_mask_words(uint64_t n_positions);
 int dkb_pack_reads(const uint8_t *seq, const uint8_t *qual, const uint64_t *offsets,
                    size_t n_reads, int min_baseq, uint32_t *bases2, uint32_t *mask1,
                    uint64_t *n_positions_out);
+/* The same from either form the BAM layer holds (seq_format as in dkb_batch_submit_reads): 0 =
+ * ASCII bases, read r at seq[offsets[r]..offsets[r+1]); 1 = BAM 4-bit codes (=ACMGRSVTWYHKDBN,
+ * high nibble first: record.seq().encoded of rust-htslib, no decode pass), every read starting
+ * on a byte boundary with (len + 1) / 2 bytes, reads back to back from seq[0].  qual is one byte
+ * per base at qual[offsets[r]..] either way.  Same stream, bit for bit, for the same reads. */
+int dkb_pack_reads_fmt(const uint8_t *seq, int seq_format, const uint8_t *qual, const uint64_t *offsets,
+                       size_t n_reads, int min_baseq, uint32_t *bases2, uint32_t *mask1,
+                       uint64_t *n_positions_out);
 
 /* ---- the flags as a ZERO LIST (a third less PCIe traffic) ----------------------- */
 /* mask1 costs 1 bit per position; with ~4 % of the positions unusable (N, low quality, read

@@ -65,15 +65,16 @@ struct Stream {
   uint64_t n_positions = 0;
 };
 
+// four_bit: seq holds BAM 4-bit codes (high nibble first, every read on a byte boundary)
 inline Stream pack_reads(const std::vector<uint8_t> &seq, const std::vector<uint8_t> &qual,
-                         const std::vector<uint64_t> &offsets, int min_baseq) {
+                         const std::vector<uint64_t> &offsets, int min_baseq, bool four_bit = false) {
   const size_t n_reads = offsets.empty() ? 0 : offsets.size() - 1;
   Stream s;
   s.n_positions = dkb_stream_positions(offsets.data(), n_reads);
   s.bases2.resize(dkb_stream_bases_words(s.n_positions) + 1);
   s.mask1.resize(dkb_stream_mask_words(s.n_positions) + 1);
-  check(dkb_pack_reads(seq.data(), qual.empty() ? nullptr : qual.data(), offsets.data(), n_reads,
-                       min_baseq, s.bases2.data(), s.mask1.data(), &s.n_positions));
+  check(dkb_pack_reads_fmt(seq.data(), four_bit ? 1 : 0, qual.empty() ? nullptr : qual.data(), offsets.data(),
+                           n_reads, min_baseq, s.bases2.data(), s.mask1.data(), &s.n_positions));
   return s;
 }
 

@@ -200,6 +200,53 @@ def test_pack_reads_isa_paths_agree(dkb, read_len, ragged, monkeypatch):
     assert outs[0][2] > (1 << 20)  # large enough for the threaded split
 
 
+def _to_bam4(seq, off):
+    """ASCII reads -> BAM 4-bit codes (=ACMGRSVTWYHKDBN, high nibble first), every read on a byte
+    boundary; the unused low nibble of an odd read's last byte gets a random code."""
+    code = np.full(256, 15, np.uint8)
+    for v, ch in enumerate(b"=ACMGRSVTWYHKDBN"):
+        code[ch] = code[ord(chr(ch).lower())] = v
+    lens = np.diff(off).astype(np.int64)
+    starts = np.concatenate([[0], np.cumsum((lens + 1) // 2)])
+    out = np.zeros(int(starts[-1]), np.uint8)
+    r = np.repeat(np.arange(len(lens)), lens)
+    i = np.arange(len(seq)) - np.repeat(off[:-1].astype(np.int64) - int(off[0]), lens)
+    byte, hi, c = starts[r] + i // 2, i % 2 == 0, code[seq]
+    np.add.at(out, byte[hi], c[hi] << 4)
+    np.add.at(out, byte[~hi], c[~hi])
+    odd = np.nonzero(lens % 2 == 1)[0]
+    out[starts[odd + 1] - 1] |= np.random.default_rng(5).integers(0, 16, len(odd)).astype(np.uint8)
+    return out
+
+
+@pytest.mark.parametrize("read_len,ragged", [(1, False), (33, False), (65, False), (150, True), (251, False)])
+def test_pack_reads_four_bit_equals_ascii(dkb, read_len, ragged, monkeypatch):
+    """dkb_pack_reads_fmt with BAM 4-bit input (what record.seq().encoded holds: no decode pass in
+    the BAM layer) writes the same stream as the ASCII form of the same reads - IUPAC codes and
+    '=' are unusable like N, empty reads, odd lengths with a padding nibble, with and without
+    qualities, on every code path and thread split."""
+    from denovo_kmer_b200 import synth
+    g = synth.make_genome(200_000, 9)
+    seq, qual, off = synth.sample_reads([g], (2_500_000 if ragged else 1_200_000) // (read_len + 1) + 100, read_len, 3,
+                                        ragged=ragged, n_rate=0.01, lowq_frac=0.1)
+    rng = np.random.default_rng(read_len)
+    seq = seq.copy()
+    idx = rng.integers(0, len(seq), len(seq) // 100)
+    seq[idx] = np.frombuffer(b"MRSVWYHKDBN=", np.uint8)[rng.integers(0, 12, len(idx))]
+    off = np.sort(np.concatenate([off, off[rng.integers(0, len(off), len(off) // 20)]]))  # empty reads
+    b4 = _to_bam4(seq, off)
+    for threads in ("1", "3"):
+        monkeypatch.setenv("DKB_PACK_THREADS", threads)
+        for isa in ("0", "1", "2"):
+            monkeypatch.setenv("DKB_PACK_ISA", isa)
+            for q in (qual, None):
+                a = dkb.pack_reads(seq, q, off, 20)
+                b = dkb.pack_reads(b4, q, off, 20, four_bit=True)
+                assert a.n_positions == b.n_positions and np.array_equal(a.bases2, b.bases2) and \
+                    np.array_equal(a.mask1, b.mask1), (read_len, threads, isa, q is None)
+    assert a.n_positions > (1 << 20)
+
+
 def test_header_is_plain_c_and_links(dkb, tmp_path):
     """include/dkb.h must compile as C11 and a C program must link against libdkb.so and
     call the host-side entry points (the boundary is a C ABI, not a C++ one)."""
@@ -327,7 +374,7 @@ def test_rust_safe_crate_uses_only_declared_symbols():
         used.add(name)
         assert name in arity, f"{name} is not declared in the -sys crate"
         assert call_args(safe, m.end() - 1) == arity[name], name
-    assert {"dkb_ctx_create", "dkb_ctx_destroy", "dkb_table_build", "dkb_batch_submit", "dkb_pack_reads",
+    assert {"dkb_ctx_create", "dkb_ctx_destroy", "dkb_table_build", "dkb_batch_submit", "dkb_pack_reads_fmt",
             "dkb_host_alloc", "dkb_finalise", "dkb_results_fetch", "dkb_comm_init",
             "dkb_reduce_push"} <= used
     methods = set(re.findall(r"pub fn (\w+)", safe))
