@@ -293,8 +293,9 @@ impl BatchPacker {
 
     /// `dkb_pack_reads_fmt` into the next buffer: `seq`/`qual` are the reads back to back, read r at
     /// `offsets[r]..offsets[r + 1]` (in bases).  `four_bit`: `seq` holds BAM 4-bit codes
-    /// (`record.seq().encoded`, every read on a byte boundary) instead of ASCII - no decode pass.  The buffer returned was last handed out two calls ago:
-    /// call [`Counter::sync`] at least every second batch before packing again.
+    /// (`record.seq().encoded`, every read on a byte boundary) instead of ASCII - no decode pass.
+    /// The buffer returned was last handed out two calls ago: call [`Counter::sync`] at least
+    /// every second batch before packing again.
     pub fn next(&mut self, seq: &[u8], four_bit: bool, qual: Option<&[u8]>, offsets: &[u64]) -> Result<&PinnedBatch> {
         let n_reads = offsets.len().saturating_sub(1);
         let n_pos = unsafe { sys::dkb_stream_positions(offsets.as_ptr(), n_reads) };
