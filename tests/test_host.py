@@ -247,6 +247,29 @@ def test_pack_reads_four_bit_equals_ascii(dkb, read_len, ragged, monkeypatch):
     assert a.n_positions > (1 << 20)
 
 
+def test_host_code_under_asan(tmp_path):
+    """csrc/dkb_host.cpp (no CUDA in it) compiled with AddressSanitizer + UBSan and driven by
+    tests/asan_host.cpp: random batches through every packer path and the zero-list coder on
+    exact-size heap buffers.  The SIMD paths use masked loads, zero-padded copies and 64-bit
+    word stores; this is what shows that none of them reads or writes past a buffer."""
+    import os
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    exe = str(tmp_path / "asan_host")
+    cc = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined",
+                         "-fno-sanitize-recover=undefined", "-o", exe,
+                         os.path.join(root, "denovo_kmer_b200", "csrc", "dkb_host.cpp"),
+                         os.path.join(root, "tests", "asan_host.cpp"), "-pthread"], capture_output=True, text=True)
+    if cc.returncode != 0 and "asan" in (cc.stderr or "").lower():
+        pytest.skip("libasan is not installed")
+    assert cc.returncode == 0, cc.stderr
+    out = subprocess.run([exe, "120"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.strip().endswith("asan ok"), (out.stdout[-500:], out.stderr[-2000:])
+
+
 def test_header_is_plain_c_and_links(dkb, tmp_path):
     """include/dkb.h must compile as C11 and a C program must link against libdkb.so and
     call the host-side entry points (the boundary is a C ABI, not a C++ one)."""
