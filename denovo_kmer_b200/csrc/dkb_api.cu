@@ -966,6 +966,12 @@ int dkb_batch_submit_sparse(dkb_ctx *ctx, const uint32_t *bases2, const uint32_t
   if (!bases2 || !zoff || (zbytes_used && !zbytes)) return fail(ctx, DKB_EINVAL, "null stream pointer");
   const size_t nb = dkb_zero_list_blocks(n_positions);
   if ((zoff[nb] & 0x7FFFFFFFu) != zbytes_used) return fail(ctx, DKB_EINVAL, "zoff[n_blocks] != zbytes_used");
+  // the expander trusts the offsets: they must ascend inside zbytes, a plain-bits block is 256 bytes
+  for (size_t b = 0; b < nb; b++) {
+    const uint32_t cur = zoff[b] & 0x7FFFFFFFu, nxt = zoff[b + 1] & 0x7FFFFFFFu;
+    if (nxt < cur || nxt > zbytes_used || ((zoff[b] & 0x80000000u) && nxt - cur != 256u))
+      return fail(ctx, DKB_EINVAL, "malformed zero list (block offsets)");
+  }
   CU(cudaSetDevice(ctx->device));
   const size_t bw = dkb_stream_bases_words(n_positions), mw = dkb_stream_mask_words(n_positions);
   dkb_ctx::Stage &st = ctx->stage[ctx->next_stage];

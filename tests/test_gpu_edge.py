@@ -374,3 +374,22 @@ def test_zero_list_submit_equals_dense_submit(dkb, orc, tuning):
         got = kc.entry_counts()
     assert np.array_equal(got.astype(np.uint64), want), tuning
     assert want.sum() > 0
+
+
+def test_malformed_zero_list_is_refused(dkb):
+    """dkb_batch_submit_sparse checks the block offsets before the expander kernel sees them."""
+    trio = synth.make_trio_host(30_000, 10, 5, 31, seed=9)
+    ent = dkb.variant_kmers(trio.variant_tuples(), 31)
+    st = dkb.pack_reads(*trio.reads[0], 20)
+    zoff, zbytes = dkb.mask_to_zero_list(st.mask1, st.n_positions)
+    with dkb.KmerCounter(31) as kc:
+        kc.build_table(ent)
+        kc.submit_sparse(st.bases2, zoff, zbytes, st.n_positions, 0)  # the well-formed list passes
+        for mutate in (lambda z: z.__setitem__(1, int(z[2]) + 1),          # offsets descend
+                       lambda z: z.__setitem__(len(z) // 2, len(zbytes) + 7),  # beyond the bytes
+                       lambda z: z.__setitem__(0, int(z[0]) | 0x80000000)):   # "plain bits" block that is not 256 bytes
+            bad = zoff.copy()
+            mutate(bad)
+            with pytest.raises(dkb.DkbError):
+                kc.submit_sparse(st.bases2, bad, zbytes, st.n_positions, 0)
+        kc.sync()
