@@ -3,9 +3,11 @@
 // stream) and the variant k-mer builder (candidate alleles + flanks ->
 // spanning k-mer entries for kernel 1).  The reference files are unmounted;
 // the semantics are DESIGN.md §2.  No CUDA in this file.
+#include <atomic>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <new>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -40,6 +42,44 @@ inline uint64_t revcomp(uint64_t fwd, int k) {
   x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
   x = __builtin_bswap64(x);
   return x >> (64 - 2 * k);
+}
+
+// fn(0) .. fn(n - 1), one item per thread, the last on the calling thread.  Nothing escapes: an
+// item that throws (out of memory) makes the call return false, and items for which no thread
+// could be started run on the calling thread.
+template <class F>
+bool run_parallel(unsigned n, F &&fn) {
+  std::atomic<bool> ok{true};
+  auto guarded = [&](unsigned t) {
+    try {
+      fn(t);
+    } catch (...) {
+      ok = false;
+    }
+  };
+  std::vector<std::thread> pool;
+  unsigned started = 0;
+  try {
+    pool.reserve(n ? n - 1 : 0);
+    for (; started + 1 < n; started++) pool.emplace_back(guarded, started);
+  } catch (...) {  // no more threads (or no memory for the pool): the rest runs here
+  }
+  for (unsigned t = started; t < n; t++) guarded(t);
+  for (auto &th : pool) th.join();
+  return ok;
+}
+
+// The ABI promises that nothing throws across it: every entry point that allocates runs its
+// body through this.
+template <class F>
+int no_throw(F &&body) {
+  try {
+    return body();
+  } catch (const std::bad_alloc &) {
+    return DKB_ENOMEM;
+  } catch (...) {
+    return DKB_EINVAL;
+  }
 }
 
 }  // namespace
@@ -326,6 +366,7 @@ int dkb_pack_reads(const uint8_t *seq, const uint8_t *qual, const uint64_t *offs
 int dkb_pack_reads_fmt(const uint8_t *seq, int seq_format, const uint8_t *qual, const uint64_t *offsets,
                        size_t n_reads, int min_baseq, uint32_t *bases2, uint32_t *mask1,
                        uint64_t *n_positions_out) {
+  return no_throw([&]() -> int {
   if (!offsets && n_reads) return DKB_EINVAL;
   if (!bases2 || !mask1) return DKB_EINVAL;
   if (n_reads && !seq) return DKB_EINVAL;
@@ -379,15 +420,10 @@ int dkb_pack_reads_fmt(const uint8_t *seq, int seq_format, const uint8_t *qual, 
       pack_range(seq, nib, qual, offsets, n_reads, min_baseq, bases2, mask1, p0, p1);
     }
   };
-  if (n_thr == 1) {
-    work(0);
-  } else {
-    std::vector<std::thread> pool;
-    for (unsigned t = 0; t < n_thr; t++) pool.emplace_back(work, t);
-    for (auto &th : pool) th.join();
-  }
+  if (!run_parallel(n_thr, work)) return DKB_ENOMEM;
   if (n_positions_out) *n_positions_out = n_pos;
   return DKB_OK;
+  });
 }
 
 // ---- dense flags -> zero list (include/dkb.h) ---------------------------------------------
@@ -433,6 +469,7 @@ size_t dkb_zero_list_blocks(uint64_t n_positions) { return (size_t)((n_positions
 
 int dkb_mask_to_zero_list(const uint32_t *mask1, uint64_t n_positions, uint32_t *zoff, uint8_t *zbytes,
                           size_t zbytes_cap, size_t *zbytes_used) {
+  return no_throw([&]() -> int {
   if (!zbytes_used || (n_positions && (!mask1 || !zoff))) return DKB_EINVAL;
   const size_t nb = dkb_zero_list_blocks(n_positions);
   if (nb >= 0x7FFFFFFFu / 256) return DKB_EINVAL;
@@ -480,13 +517,7 @@ int dkb_mask_to_zero_list(const uint32_t *mask1, uint64_t n_positions, uint32_t 
       }
     }
   };
-  auto parallel = [&](auto &&fn) {
-    if (n_thr == 1) return fn(0u);
-    std::vector<std::thread> pool;
-    for (unsigned t = 0; t < n_thr; t++) pool.emplace_back(fn, t);
-    for (auto &th : pool) th.join();
-  };
-  parallel(code);
+  if (!run_parallel(n_thr, code)) return DKB_ENOMEM;
   size_t total = 0;
   for (size_t i = 0; i < nb; i++) {
     zoff[i] = (uint32_t)total | (len[i] & ZL_RAW_BIT);
@@ -496,19 +527,21 @@ int dkb_mask_to_zero_list(const uint32_t *mask1, uint64_t n_positions, uint32_t 
   *zbytes_used = total;
   if (!fill) return DKB_OK;  // sizing call
   if (total > zbytes_cap) return DKB_EINVAL;
-  parallel([&](unsigned t) {
+  run_parallel(n_thr, [&](unsigned t) {
     const size_t a = (size_t)t * per, b = a + per < nb ? a + per : nb;
     if (a >= b) return;
     const size_t first = zoff[a] & ~ZL_RAW_BIT, last = b < nb ? (zoff[b] & ~ZL_RAW_BIT) : total;
     memcpy(zbytes + first, scratch[t].data(), last - first);
   });
   return DKB_OK;
+  });
 }
 
 int dkb_variant_kmers(const char *const *left, const char *const *ref, const char *const *alt,
                       const char *const *right, size_t n_variants, int k, int drop_shared,
                       uint64_t *keys, uint32_t *variant_ids, uint8_t *allele_ids,
                       uint16_t *win_index, uint16_t *win_count, size_t *n_out) {
+  return no_throw([&]() -> int {
   if (!n_out || k < DKB_MIN_K || k > DKB_MAX_K) return DKB_EINVAL;
   if (n_variants && (!left || !ref || !alt || !right)) return DKB_EINVAL;
   size_t n = 0;
@@ -580,6 +613,7 @@ int dkb_variant_kmers(const char *const *left, const char *const *ref, const cha
   }
   *n_out = n;
   return DKB_OK;
+  });
 }
 
 }  // extern "C"
