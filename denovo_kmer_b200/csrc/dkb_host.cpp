@@ -407,12 +407,21 @@ int dkb_pack_reads_fmt(const uint8_t *seq, int seq_format, const uint8_t *qual, 
   const uint64_t per = ((n_pos + n_thr - 1) / n_thr + 127) / 128 * 128;
   auto work = [&](unsigned t) {
     const uint64_t p0 = (uint64_t)t * per, p1 = p0 + per < n_pos ? p0 + per : n_pos;
-    // this thread's words (the tail thread also clears the padding words)
-    const size_t b0 = (size_t)(p0 / 16), b1 = t + 1 == n_thr ? bw : (size_t)((p0 + per) / 16);
-    const size_t m0 = (size_t)(p0 / 32), m1 = t + 1 == n_thr ? mw : (size_t)((p0 + per) / 32);
-    if (b0 < bw) memset(bases2 + b0, 0, ((b1 < bw ? b1 : bw) - b0) * 4);
-    if (m0 < mw) memset(mask1 + m0, 0, ((m1 < mw ? m1 : mw) - m0) * 4);
-    if (p0 < p1 && n_reads) {
+    // this thread's words.  The packers store every word that lies wholly inside [p0, p1) and the
+    // one p1 falls into; what is cleared here - before they run - is the rest: from the 64-bit word
+    // p1 falls into to the end of the thread's words (the stream's padding, for the tail thread),
+    // or everything when the range holds no position.
+    const bool packs = p0 < p1 && n_reads;
+    size_t b0 = (size_t)(p0 / 16), m0 = (size_t)(p0 / 32);
+    const size_t b1 = t + 1 == n_thr ? bw : (size_t)((p0 + per) / 16);
+    const size_t m1 = t + 1 == n_thr ? mw : (size_t)((p0 + per) / 32);
+    if (packs) {
+      b0 = (size_t)(p1 / 32) * 2;
+      m0 = (size_t)(p1 / 64) * 2;
+    }
+    if (b0 < bw && b0 < b1) memset(bases2 + b0, 0, ((b1 < bw ? b1 : bw) - b0) * 4);
+    if (m0 < mw && m0 < m1) memset(mask1 + m0, 0, ((m1 < mw ? m1 : mw) - m0) * 4);
+    if (packs) {
 #ifdef DKB_HAVE_SIMD_PACK
       if (simd == 2) return pack_range_avx512(seq, nib, qual, offsets, n_reads, min_baseq, bases2, mask1, p0, p1);
       if (simd == 1) return pack_range_avx2(seq, nib, qual, offsets, n_reads, min_baseq, bases2, mask1, p0, p1);
