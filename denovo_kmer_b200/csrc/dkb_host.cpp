@@ -371,19 +371,6 @@ int dkb_pack_reads_fmt(const uint8_t *seq, int seq_format, const uint8_t *qual, 
   if (!bases2 || !mask1) return DKB_EINVAL;
   if (n_reads && !seq) return DKB_EINVAL;
   if (seq_format != 0 && seq_format != 1) return DKB_EINVAL;
-  for (size_t r = 0; r < n_reads; r++)
-    if (offsets[r + 1] < offsets[r]) return DKB_EINVAL;
-  // BAM keeps every read's 4-bit codes byte-aligned: (len + 1) / 2 bytes per read, back to back
-  std::vector<uint64_t> nib_of;
-  if (seq_format == 1) {
-    nib_of.resize(n_reads);
-    uint64_t b = 0;
-    for (size_t r = 0; r < n_reads; r++) {
-      nib_of[r] = b;
-      b += (offsets[r + 1] - offsets[r] + 1) / 2;
-    }
-  }
-  const uint64_t *nib = seq_format == 1 ? nib_of.data() : nullptr;
   const uint64_t n_pos = dkb_stream_positions(offsets, n_reads);
   const size_t bw = dkb_stream_bases_words(n_pos), mw = dkb_stream_mask_words(n_pos);
   // 0 scalar, 1 AVX2 + BMI2 (32 bases per step), 2 AVX-512 BW + BMI2 (64 per step); the best the
@@ -404,6 +391,48 @@ int dkb_pack_reads_fmt(const uint8_t *seq, int seq_format, const uint8_t *qual, 
   if (const char *e = getenv("DKB_PACK_THREADS")) n_thr = atoi(e) > 0 ? (unsigned)atoi(e) : n_thr;
   if (n_thr < 1 || n_pos < (1u << 20)) n_thr = 1;
   if (n_thr > (n_pos >> 20)) n_thr = (unsigned)(n_pos >> 20) ? (unsigned)(n_pos >> 20) : 1;  // >= 1 M positions per thread
+  // The offsets are checked before anything is read through them, and - BAM keeps every read's
+  // 4-bit codes byte-aligned, (len + 1) / 2 bytes per read, back to back - the byte offset of
+  // every read is their prefix sum: both by chunks of reads, on the same threads as the packing
+  // (at 150-base reads a serial pass over the offsets cost a third of the packing time).
+  std::vector<uint64_t> nib_of;
+  if (seq_format == 1) nib_of.resize(n_reads);
+  {
+    const size_t rper = (n_reads + n_thr - 1) / n_thr;
+    std::vector<uint64_t> chunk_bytes(n_thr, 0);
+    std::atomic<bool> bad{false};
+    if (!run_parallel(n_thr, [&](unsigned t) {
+          const size_t a = (size_t)t * rper, b = a + rper < n_reads ? a + rper : n_reads;
+          uint64_t bytes = 0;
+          bool dec = false;
+          for (size_t r = a; r < b; r++) {
+            dec |= offsets[r + 1] < offsets[r];
+            bytes += (offsets[r + 1] - offsets[r] + 1) / 2;
+          }
+          if (dec) bad = true;
+          chunk_bytes[t] = bytes;
+        }))
+      return DKB_ENOMEM;
+    if (bad) return DKB_EINVAL;
+    if (seq_format == 1) {
+      uint64_t acc = 0;
+      for (unsigned t = 0; t < n_thr; t++) {
+        const uint64_t c = chunk_bytes[t];
+        chunk_bytes[t] = acc;
+        acc += c;
+      }
+      if (!run_parallel(n_thr, [&](unsigned t) {
+            const size_t a = (size_t)t * rper, b = a + rper < n_reads ? a + rper : n_reads;
+            uint64_t at = chunk_bytes[t];
+            for (size_t r = a; r < b; r++) {
+              nib_of[r] = at;
+              at += (offsets[r + 1] - offsets[r] + 1) / 2;
+            }
+          }))
+        return DKB_ENOMEM;
+    }
+  }
+  const uint64_t *nib = seq_format == 1 ? nib_of.data() : nullptr;
   const uint64_t per = ((n_pos + n_thr - 1) / n_thr + 127) / 128 * 128;
   auto work = [&](unsigned t) {
     const uint64_t p0 = (uint64_t)t * per, p1 = p0 + per < n_pos ? p0 + per : n_pos;

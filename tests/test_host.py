@@ -247,6 +247,23 @@ def test_pack_reads_four_bit_equals_ascii(dkb, read_len, ragged, monkeypatch):
     assert a.n_positions > (1 << 20)
 
 
+def test_pack_reads_refuses_descending_offsets(dkb, monkeypatch):
+    """Offsets are checked (by chunks of reads, on the packing threads) before any read is
+    touched through them: a descending pair anywhere is DKB_EINVAL, for both input forms."""
+    n = 40_000
+    off = np.arange(n + 1, dtype=np.uint64) * 40
+    seq = np.full(int(off[-1]), ord("A"), np.uint8)
+    for threads in ("1", "4"):
+        monkeypatch.setenv("DKB_PACK_THREADS", threads)
+        assert dkb.pack_reads(seq, None, off, 20).n_positions == int(off[-1]) + n
+        for where in (1, n // 2, n - 1):
+            bad = off.copy()
+            bad[where] = bad[where + 1] + 5
+            for four_bit in (False, True):
+                with pytest.raises(dkb.DkbError):
+                    dkb.pack_reads(seq, None, bad, 20, four_bit=four_bit)
+
+
 def test_host_code_under_asan(tmp_path):
     """csrc/dkb_host.cpp (no CUDA in it) compiled with AddressSanitizer + UBSan and driven by
     tests/asan_host.cpp: random batches through every packer path and the zero-list coder on
