@@ -386,11 +386,14 @@ int dkb_pack_reads_fmt(const uint8_t *seq, int seq_format, const uint8_t *qual, 
 #endif
   (void)simd;
   // output words are split between threads on 128-position boundaries: no sharing
+  // every hardware thread up to 32, at least 1 M positions each; DKB_PACK_THREADS=n means exactly n
+  // (up to 64), whatever the batch size
   unsigned n_thr = std::thread::hardware_concurrency();
   if (n_thr > 32) n_thr = 32;
-  if (const char *e = getenv("DKB_PACK_THREADS")) n_thr = atoi(e) > 0 ? (unsigned)atoi(e) : n_thr;
-  if (n_thr < 1 || n_pos < (1u << 20)) n_thr = 1;
-  if (n_thr > (n_pos >> 20)) n_thr = (unsigned)(n_pos >> 20) ? (unsigned)(n_pos >> 20) : 1;  // >= 1 M positions per thread
+  if (n_thr > (n_pos >> 20)) n_thr = (unsigned)(n_pos >> 20);
+  if (const char *e = getenv("DKB_PACK_THREADS"))
+    if (atoi(e) > 0) n_thr = atoi(e) > 64 ? 64u : (unsigned)atoi(e);
+  if (n_thr < 1) n_thr = 1;
   // The offsets are checked before anything is read through them, and - BAM keeps every read's
   // 4-bit codes byte-aligned, (len + 1) / 2 bytes per read, back to back - the byte offset of
   // every read is their prefix sum: both by chunks of reads, on the same threads as the packing
@@ -517,8 +520,9 @@ int dkb_mask_to_zero_list(const uint32_t *mask1, uint64_t n_positions, uint32_t 
   std::vector<uint32_t> len(nb);
   unsigned n_thr = std::thread::hardware_concurrency();
   if (n_thr > 32) n_thr = 32;
-  if (const char *e = getenv("DKB_PACK_THREADS")) n_thr = atoi(e) > 0 ? (unsigned)atoi(e) : n_thr;
   if (n_thr > nb / 512) n_thr = (unsigned)(nb / 512);  // >= 1 M positions per thread
+  if (const char *e = getenv("DKB_PACK_THREADS"))  // exactly n (up to 64), whatever the size
+    if (atoi(e) > 0) n_thr = atoi(e) > 64 ? 64u : (unsigned)atoi(e);
   if (n_thr < 1) n_thr = 1;
   const size_t per = (nb + n_thr - 1) / n_thr;
   const bool fill = zbytes != nullptr;

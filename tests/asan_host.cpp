@@ -14,7 +14,7 @@ int main(int argc, char **argv) {
   const int n_iter = argc > 1 ? atoi(argv[1]) : 400;
   std::mt19937_64 g(7);
   const char *isas[] = {"0", "1", "2"};
-  const char *thr[] = {"1", "3"};
+  const char *thr[] = {"1", "3", "16"};
   for (int it = 0; it < n_iter; it++) {
     size_t n_reads = g() % 3000;
     int maxlen = 1 + g() % 300;

@@ -186,7 +186,7 @@ def test_pack_reads_isa_paths_agree(dkb, read_len, ragged, monkeypatch):
     qual[idx] = rng.integers(0, 256, len(idx)).astype(np.uint8)
     off = np.sort(np.concatenate([off, off[rng.integers(0, len(off), len(off) // 20)]]))  # empty reads
     for offs in (off, off[7:-5]):
-        for threads in ("1", "3"):
+        for threads in ("1", "3", "16"):
             monkeypatch.setenv("DKB_PACK_THREADS", threads)
             for mq, use_q in ((20, True), (0, True), (255, True), (256, True), (-3, True), (20, False)):
                 outs = []
@@ -235,7 +235,7 @@ def test_pack_reads_four_bit_equals_ascii(dkb, read_len, ragged, monkeypatch):
     seq[idx] = np.frombuffer(b"MRSVWYHKDBN=", np.uint8)[rng.integers(0, 12, len(idx))]
     off = np.sort(np.concatenate([off, off[rng.integers(0, len(off), len(off) // 20)]]))  # empty reads
     b4 = _to_bam4(seq, off)
-    for threads in ("1", "3"):
+    for threads in ("1", "3", "16"):
         monkeypatch.setenv("DKB_PACK_THREADS", threads)
         for isa in ("0", "1", "2"):
             monkeypatch.setenv("DKB_PACK_ISA", isa)
